@@ -1,0 +1,160 @@
+/*
+ * tray_cuda.h -- C ABI of libtraycuda.so, the B200 (sm_100a) path-tracing backend for fortio/tray.
+ *
+ * This is the drop-in boundary: the Go package `ray` keeps its API
+ * (ray.New, Tracer fields, (*Tracer).Render / RenderLines, Scene/Sphere/materials, Camera) and
+ * its cgo shim binds exactly these entry points (see INTEGRATION.md for the stub). Plain
+ * pointers and sizes only; the library copies every input before returning and keeps no
+ * caller pointer (cgo pointer rules). All functions return 0 on success or a negative
+ * TRAY_E_* code; the message is available from tray_last_error().
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   tray_render        <- (*Tracer).Render        ray/tracer.go:48-118   (fan-out + accumulate + sRGB store)
+ *                      <- (*Tracer).RenderLines   ray/tracer.go:120-155  (rows [y0,y1), stream index idx)
+ *   tray_scene_upload  <- Scene{Objects,Background} walk: Scene.Hit ray/objects.go:37-46,
+ *                         Sphere ray/objects.go:75-79, Lambertian/Metal/Dielectric ray/materials.go:9-44
+ *   tray_camera        <- Camera after Initialize  ray/camera.go:9-39,43-105 (Initialize stays on the host)
+ *   tray_first_hit     <- Scene.Hit + Sphere.Hit   ray/objects.go:37-46,81-104 (parity probe, RNG-free)
+ *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
+ *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
+ */
+#ifndef TRAY_CUDA_H
+#define TRAY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRAY_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TRAY_API __attribute__((visibility("default")))
+#else
+#define TRAY_API
+#endif
+
+/* error codes */
+#define TRAY_OK 0
+#define TRAY_E_INVALID (-1)   /* bad argument */
+#define TRAY_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define TRAY_E_NO_SCENE (-3)  /* tray_render before tray_scene_upload */
+#define TRAY_E_UNSUPPORTED (-4)
+#define TRAY_E_NO_DEVICE (-5) /* no usable sm_100 device: there is NO CPU fallback */
+
+/* material kinds (Material implementations, ray/materials.go) */
+#define TRAY_MAT_LAMBERTIAN 0 /* params: albedo r,g,b, unused        */
+#define TRAY_MAT_METAL 1      /* params: albedo r,g,b, fuzz          */
+#define TRAY_MAT_DIELECTRIC 2 /* params: ref_idx, unused x3          */
+
+/* RNG stream conventions */
+#define TRAY_STREAM_REFERENCE 0  /* one sequential stream per reference chunk, exactly ray/tracer.go:87-121
+                                    (conformance mode: one warp per chunk, slow by construction) */
+#define TRAY_STREAM_PER_SAMPLE 1 /* stream = rand.NewIdx((y*W+x)*spp+s, seed): throughput mode, result
+                                    independent of partitioning and GPU count */
+
+/* arithmetic modes */
+#define TRAY_FP64_FMA 0    /* float64; Sphere.Hit discriminant uses fused multiply-add (11 FP64 ops/test) */
+#define TRAY_FP64_STRICT 1 /* float64; every op rounded separately = Go/amd64 semantics (17 FP64 ops/test) */
+#define TRAY_FP32 2        /* float32 fast path (reported separately, PSNR vs fp64) */
+
+/* multi-GPU partitioning inside one context */
+#define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */
+#define TRAY_SPLIT_SAMPLES 1 /* each GPU renders samples s == g (mod G); partial sums reduced over NVLink */
+
+typedef struct tray_ctx tray_ctx;
+
+/* Flattened scene: SoA over spheres, in Scene.Objects order (ties resolve to the lowest index). */
+typedef struct {
+    int32_t n;                 /* number of spheres */
+    const double *cx, *cy, *cz; /* centres */
+    const double *radius;
+    const uint8_t *mat_kind;   /* TRAY_MAT_* */
+    const double *mat_params;  /* n x 4 */
+    double bg_a[3], bg_b[3];   /* AmbientLight ColorA / ColorB (ray/objects.go:64-73) */
+} tray_scene_desc;
+
+/* Camera AFTER Camera.Initialize (ray/camera.go:43-105): derived vectors, computed on the host. */
+typedef struct {
+    double position[3];
+    double pixel00[3], pixel_x[3], pixel_y[3];
+    double defocus_u[3], defocus_v[3];
+    double aperture, focus_distance, focal_length;
+} tray_camera;
+
+typedef struct {
+    int32_t width, height;
+    int32_t spp;        /* NumRaysPerPixel (>0, already defaulted) */
+    int32_t max_depth;  /* MaxDepth (>0, already defaulted) */
+    double ray_radius;  /* RayRadius */
+    uint64_t seed;      /* non-zero (the host shim draws one when the user passes 0) */
+    int32_t y0, y1;     /* rows to render, [y0,y1); Render uses 0,height */
+    int32_t stream_mode;  /* TRAY_STREAM_* */
+    int32_t num_workers;  /* REFERENCE mode: NumWorkers of the fan-out (ray/tracer.go:85-116);
+                             <=0 with stream_idx>=0 means a single RenderLines(stream_idx,y0,y1) stream */
+    int64_t stream_idx;   /* REFERENCE mode RenderLines idx; -1 = derive from chunking */
+    int32_t precision;    /* TRAY_FP64_FMA | TRAY_FP64_STRICT | TRAY_FP32 */
+    int32_t split_mode;   /* TRAY_SPLIT_* (only matters when the context has >1 device) */
+    int32_t shard_index, shard_count; /* multi-process tile sharding: this context renders only the
+                             row bands b with b % shard_count == shard_index (0,1 or 0,0 = everything);
+                             rows of other shards in the output are left untouched */
+    int32_t reserved[5];
+} tray_params;
+
+typedef struct {
+    uint64_t paths;        /* samples traced (w*rows*spp) */
+    uint64_t segments;     /* Scene.Hit calls, primary included */
+    uint64_t sphere_tests; /* Sphere.Hit evaluations */
+    uint64_t depth_exhausted; /* paths that ran into MaxDepth */
+    double kernel_ms;      /* device time of the trace+resolve kernels (CUDA events, max over devices) */
+    double total_ms;       /* wall time inside tray_render, copies included */
+    int32_t launches;      /* kernels launched by this call */
+    int32_t n_devices;
+    double trace_kernel_ms; /* device time of the trace kernels alone */
+    double reserved[3];
+} tray_stats;
+
+/* Creates a context on the given CUDA devices (devices==NULL or n_devices<=0: device 0). */
+TRAY_API int tray_init(const int *devices, int n_devices, tray_ctx **out);
+TRAY_API void tray_destroy(tray_ctx *ctx);
+TRAY_API const char *tray_last_error(tray_ctx *ctx); /* ctx may be NULL: last init error */
+TRAY_API int tray_abi_version(void);
+
+/* Copies the scene to every device of the context. May be called again to replace the scene. */
+TRAY_API int tray_scene_upload(tray_ctx *ctx, const tray_scene_desc *scene);
+
+/* Renders rows [y0,y1) into rgba_out (R,G,B,255 per pixel; row y at rgba_out + y*stride, i.e.
+ * rgba_out is &img.Pix[0]). rgba_out may be NULL: the image then stays on the device
+ * (fetch with tray_read_image). stats may be NULL. */
+TRAY_API int tray_render(tray_ctx *ctx, const tray_camera *cam, const tray_params *params,
+                uint8_t *rgba_out, size_t stride, tray_stats *stats);
+
+/* Copies the last rendered image / linear-HDR means (w*h*3 doubles, colorSum*(1/N) before sRGB). */
+TRAY_API int tray_read_image(tray_ctx *ctx, uint8_t *rgba_out, size_t stride);
+TRAY_API int tray_read_hdr(tray_ctx *ctx, double *hdr_out);
+
+/* RNG-independent parity probe: closest hit of every pixel-centre pinhole primary ray.
+ * id -1 / t +Inf on a miss. Arrays are width*height (normal: x3). */
+TRAY_API int tray_first_hit(tray_ctx *ctx, const tray_camera *cam, int32_t width, int32_t height, int32_t precision,
+                   int32_t *id, double *t, double *normal, uint8_t *front);
+
+/* Parity probe for the device generators: kind 0 Uint64 (as double bit patterns in out64),
+ * 1 Float64, 2 NormFloat64, 3 UnitVector (3 per draw), 4 InDisc(radius) (2 per draw). */
+TRAY_API int tray_rng_dump(tray_ctx *ctx, int32_t kind, uint64_t idx, uint64_t seed, double radius, int32_t n, double *out);
+
+/* Parity probe for the on-device sRGB store (ColorF.ToSRGBA, ray/vec3.go:173-180). */
+TRAY_API int tray_linear_to_srgb(tray_ctx *ctx, const double *x, int32_t n, uint8_t *out);
+
+/* Pixels completed by the render in flight (or the last one); safe from another thread. */
+TRAY_API uint64_t tray_progress(tray_ctx *ctx);
+
+/* Measured FP64 (kind 0: DFMA, 1: DADD+DMUL) / FP32 (kind 2: FFMA) issue-bound peak in TFLOP/s on device 0
+ * of the context and the SM clock seen (roofline denominator; bench.py reports it). */
+TRAY_API int tray_measure_peak(tray_ctx *ctx, int32_t kind, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAY_CUDA_H */

@@ -1,0 +1,245 @@
+"""ctypes binding of the CPU oracle (oracle/tray_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs. Never imported by the tray_b200 package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "tray_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
+    return _SO
+
+
+class Scene(C.Structure):
+    _fields_ = [("n", C.c_int32),
+                ("cx", C.c_void_p), ("cy", C.c_void_p), ("cz", C.c_void_p), ("r", C.c_void_p),
+                ("kind", C.c_void_p), ("params", C.c_void_p),
+                ("bg_a", C.c_double * 3), ("bg_b", C.c_double * 3)]
+
+
+class Camera(C.Structure):
+    _fields_ = [(k, C.c_double * 3) for k in
+                ("position", "pixel00", "pixel_x", "pixel_y", "defocus_u", "defocus_v")] + \
+               [("aperture", C.c_double), ("focus_distance", C.c_double), ("focal_length", C.c_double)]
+
+
+class CameraIn(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("look_at", C.c_double * 3), ("up", C.c_double * 3),
+                ("vfov", C.c_double), ("focal_length", C.c_double), ("focus_distance", C.c_double),
+                ("aperture", C.c_double)]
+
+
+class Params(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
+                ("ray_radius", C.c_double), ("seed", C.c_uint64), ("num_workers", C.c_int32),
+                ("stream_mode", C.c_int32), ("fma_mode", C.c_int32), ("threads", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("paths", "segments", "sphere_tests", "rng_draws", "max_depth_hits")]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_linear_to_srgb.restype = C.c_uint8
+        _lib.oracle_linear_to_srgb.argtypes = [C.c_double]
+        for f in ("oracle_go_log", "oracle_go_exp", "oracle_go_tan"):
+            getattr(_lib, f).restype = C.c_double
+            getattr(_lib, f).argtypes = [C.c_double]
+        _lib.oracle_reflectance.restype = C.c_double
+        _lib.oracle_reflectance.argtypes = [C.c_double, C.c_double]
+        _lib.oracle_rich_scene.restype = C.c_int
+        _lib.oracle_rich_scene.argtypes = [C.c_uint64, C.c_int] + [C.c_void_p] * 6
+        _lib.oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.oracle_render_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.oracle_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+        _lib.oracle_camera_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.oracle_rng_u64.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        _lib.oracle_rng_f64.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        _lib.oracle_rng_norm.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        _lib.oracle_rng_unit_vectors.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        _lib.oracle_rng_in_disc.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_void_p]
+        _lib.oracle_sphere_hit.restype = C.c_int
+        _lib.oracle_sphere_hit.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_scatter.restype = C.c_int
+        _lib.oracle_scatter.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64] + [C.c_void_p] * 4 + \
+                                       [C.c_int] + [C.c_void_p] * 4
+        _lib.oracle_ray_color.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
+                                          C.c_int, C.c_void_p]
+        _lib.oracle_set_variants.argtypes = [C.c_int, C.c_int]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _d3(v):
+    return np.ascontiguousarray(v, dtype=np.float64)
+
+
+class FlatScene:
+    """Flat SoA scene: the same arrays the C-ABI takes. Keeps the numpy buffers alive."""
+
+    def __init__(self, cx, cy, cz, r, kind, params, bg_a=(1.0, 1.0, 1.0), bg_b=(0.4, 0.65, 1.0)):
+        self.cx, self.cy, self.cz, self.r = (np.ascontiguousarray(a, dtype=np.float64) for a in (cx, cy, cz, r))
+        self.kind = np.ascontiguousarray(kind, dtype=np.uint8)
+        self.params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 4)
+        self.n = len(self.cx)
+        self.bg_a, self.bg_b = tuple(bg_a), tuple(bg_b)
+
+    def c(self):
+        s = Scene()
+        s.n = self.n
+        s.cx, s.cy, s.cz, s.r = _p(self.cx), _p(self.cy), _p(self.cz), _p(self.r)
+        s.kind, s.params = _p(self.kind), _p(self.params)
+        s.bg_a[:] = self.bg_a
+        s.bg_b[:] = self.bg_b
+        return s
+
+
+def rich_scene(seed, half=11):
+    """RichScene(rand.New(seed)) (ray/objects.go:132-175)."""
+    cap = (2 * half) ** 2 + 4
+    cx, cy, cz, r = (np.zeros(cap) for _ in range(4))
+    kind = np.zeros(cap, dtype=np.uint8)
+    params = np.zeros((cap, 4))
+    n = lib().oracle_rich_scene(seed, half, _p(cx), _p(cy), _p(cz), _p(r), _p(kind), _p(params))
+    return FlatScene(cx[:n].copy(), cy[:n].copy(), cz[:n].copy(), r[:n].copy(), kind[:n].copy(), params[:n].copy())
+
+
+RICH_CAMERA = dict(position=(13, 2, 3), look_at=(0, 0, 0), up=(0, 1, 0), vfov=20.0, aperture=0.1,
+                   focal_length=10.0, focus_distance=10.0)  # ray/camera.go:144-154
+
+
+def camera_init(width, height, position=(0, 0, 0), look_at=(0, 0, 0), up=(0, 0, 0), vfov=0.0,
+                focal_length=0.0, focus_distance=0.0, aperture=0.0, tan_mode=0):
+    ci = CameraIn()
+    ci.position[:] = position
+    ci.look_at[:] = look_at
+    ci.up[:] = up
+    ci.vfov, ci.focal_length, ci.focus_distance, ci.aperture = vfov, focal_length, focus_distance, aperture
+    out = Camera()
+    lib().oracle_camera_init(C.byref(ci), width, height, tan_mode, C.byref(out))
+    return out
+
+
+def make_params(width, height, spp=1, max_depth=10, ray_radius=0.5, seed=1, num_workers=1, stream_mode=0,
+                fma_mode=0, threads=0):
+    p = Params()
+    p.width, p.height, p.spp, p.max_depth = width, height, spp, max_depth
+    p.ray_radius, p.seed, p.num_workers = ray_radius, seed, num_workers
+    p.stream_mode, p.fma_mode, p.threads = stream_mode, fma_mode, threads
+    return p
+
+
+def render(scene, cam, params, want_hdr=False, out=None):
+    """Tracer.Render (ray/tracer.go:48-118). Returns (rgba[h,w,4] u8, hdr[h,w,3] f64 | None, stats dict)."""
+    h, w = params.height, params.width
+    rgba = out if out is not None else np.zeros((h, w, 4), dtype=np.uint8)
+    hdr = np.zeros((h, w, 3)) if want_hdr else None
+    st = Stats()
+    sc = scene.c()
+    rc = lib().oracle_render(C.byref(sc), C.byref(cam), C.byref(params), _p(rgba), w * 4,
+                             _p(hdr) if want_hdr else None, C.byref(st))
+    if rc != 0:
+        raise RuntimeError("oracle_render failed: %d" % rc)
+    return rgba, hdr, st.as_dict()
+
+
+def render_lines(scene, cam, params, idx, y0, y1, rgba, hdr=None):
+    """Tracer.RenderLines (ray/tracer.go:120-155) into an existing image."""
+    st = Stats()
+    sc = scene.c()
+    lib().oracle_render_lines(C.byref(sc), C.byref(cam), C.byref(params), idx, y0, y1, _p(rgba), params.width * 4,
+                              _p(hdr) if hdr is not None else None, C.byref(st))
+    return st.as_dict()
+
+
+def first_hit(scene, cam, width, height, fma_mode=0):
+    ids = np.zeros((height, width), dtype=np.int32)
+    t = np.zeros((height, width))
+    nrm = np.zeros((height, width, 3))
+    front = np.zeros((height, width), dtype=np.uint8)
+    sc = scene.c()
+    lib().oracle_first_hit(C.byref(sc), C.byref(cam), width, height, fma_mode, _p(ids), _p(t), _p(nrm), _p(front))
+    return ids, t, nrm, front
+
+
+def rng_u64(idx, seed, n):
+    out = np.zeros(n, dtype=np.uint64)
+    lib().oracle_rng_u64(idx, seed, n, _p(out))
+    return out
+
+
+def rng_f64(idx, seed, n):
+    out = np.zeros(n)
+    lib().oracle_rng_f64(idx, seed, n, _p(out))
+    return out
+
+
+def rng_norm(idx, seed, n):
+    out = np.zeros(n)
+    lib().oracle_rng_norm(idx, seed, n, _p(out))
+    return out
+
+
+def rng_unit_vectors(idx, seed, n):
+    out = np.zeros((n, 3))
+    lib().oracle_rng_unit_vectors(idx, seed, n, _p(out))
+    return out
+
+
+def rng_in_disc(idx, seed, radius, n):
+    out = np.zeros((n, 2))
+    lib().oracle_rng_in_disc(idx, seed, radius, n, _p(out))
+    return out
+
+
+def sphere_hit(center, radius, origin, direction, tmin, tmax, fma_mode=0):
+    t = C.c_double()
+    front = C.c_int()
+    p, n = np.zeros(3), np.zeros(3)
+    ok = lib().oracle_sphere_hit(_p(_d3(center)), radius, _p(_d3(origin)), _p(_d3(direction)), tmin, tmax, fma_mode,
+                                 C.byref(t), _p(p), _p(n), C.byref(front))
+    return (bool(ok), t.value, p, n, bool(front.value))
+
+
+def scatter(kind, prm, idx, seed, rin_o, rin_d, point, normal, front):
+    att, oo, od = np.zeros(3), np.zeros(3), np.zeros(3)
+    draws = C.c_uint64()
+    prm = np.ascontiguousarray(prm, dtype=np.float64)
+    did = lib().oracle_scatter(kind, _p(prm), idx, seed, _p(_d3(rin_o)), _p(_d3(rin_d)), _p(_d3(point)),
+                               _p(_d3(normal)), int(front), _p(att), _p(oo), _p(od), C.byref(draws))
+    return bool(did), att, oo, od, int(draws.value)
+
+
+def ray_color(scene, origin, direction, depth, idx=0, seed=42, fma_mode=0):
+    rgb = np.zeros(3)
+    sc = scene.c()
+    lib().oracle_ray_color(C.byref(sc), _p(_d3(origin)), _p(_d3(direction)), depth, idx, seed, fma_mode, _p(rgb))
+    return rgb
+
+
+def linear_to_srgb(x):
+    return int(lib().oracle_linear_to_srgb(float(x)))

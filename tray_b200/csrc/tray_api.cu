@@ -1,0 +1,723 @@
+// tray_api.cu -- host side of libtraycuda.so: the C ABI declared in include/tray_cuda.h.
+// Owns device memory, streams and events; copies every caller buffer before returning.
+// There is deliberately NO CPU fallback: without a usable sm_100 device every entry point fails.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tray_cuda.h"
+#include "tray_kernels.cuh"
+
+using namespace tray;
+
+namespace {
+
+thread_local std::string g_init_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw std::runtime_error(buf_);                                                        \
+        }                                                                                          \
+    } while (0)
+
+// ---- host copies of the deterministic log/exp used to build the sRGB threshold table --------
+// (same FreeBSD-msun forms as tray_device.cuh; host build uses -ffp-contract=off)
+double h_log(double x) {
+    const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10;
+    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
+                 L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
+                 L7 = 1.479819860511658591e-01;
+    int ki;
+    double f1 = std::frexp(x, &ki);
+    if (f1 < 0.70710678118654752440) { f1 *= 2; ki--; }
+    double f = f1 - 1, k = (double)ki;
+    double s = f / (2 + f), s2 = s * s, s4 = s2 * s2;
+    double t1 = s2 * (L1 + s4 * (L3 + s4 * (L5 + s4 * L7)));
+    double t2 = s4 * (L2 + s4 * (L4 + s4 * L6));
+    double R = t1 + t2, hfsq = 0.5 * f * f;
+    return k * Ln2Hi - ((hfsq - (s * (hfsq + R) + k * Ln2Lo)) - f);
+}
+double h_exp(double x) {
+    const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10, Log2e = 1.44269504088896338700e+00;
+    const double NearZero = 1.0 / (1 << 28);
+    const double P1 = 1.66666666666666657415e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+                 P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    if (-NearZero < x && x < NearZero) return 1 + x;
+    int k = 0;
+    if (x < 0) k = (int)(Log2e * x - 0.5);
+    else if (x > 0) k = (int)(Log2e * x + 0.5);
+    double hi = x - (double)k * Ln2Hi, lo = (double)k * Ln2Lo;
+    double r = hi - lo, t = r * r;
+    double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    double y = 1 - ((lo - (r * c) / (2 - c)) - hi);
+    return std::ldexp(y, k);
+}
+// tcolor.LinearToSrgb (third-party, call site ray/vec3.go:175-177; pinned by ray/vec3_test.go:264-289)
+int h_linear_to_srgb(double x) {
+    if (!(x > 0)) return 0;
+    if (x >= 1) return 255;
+    double s = x <= 0.0031308 ? 12.92 * x : 1.055 * h_exp((1 / 2.4) * h_log(x)) - 0.055;
+    return (int)std::round(255 * s);
+}
+// thr[k] = smallest double x with LinearToSrgb(x) >= k (bisection on the bit pattern; the map is monotone).
+void build_srgb_thresholds(double* thr) {
+    thr[0] = 0.0;
+    for (int k = 1; k <= 255; k++) {
+        uint64_t lo = 0, hi;  // lo: conv < k ; hi: conv >= k
+        double one = 1.0;
+        memcpy(&hi, &one, 8);
+        while (hi - lo > 1) {
+            uint64_t mid = lo + (hi - lo) / 2;
+            double x;
+            memcpy(&x, &mid, 8);
+            if (h_linear_to_srgb(x) >= k) hi = mid; else lo = mid;
+        }
+        memcpy(&thr[k], &hi, 8);
+    }
+}
+
+struct Device {
+    int dev = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_trace_end = nullptr, ev_end = nullptr;
+    // scene
+    int n = 0, n_pad = 0;
+    double4* geo_d = nullptr; float4* geo_f = nullptr;
+    double* radius_d = nullptr; float* radius_f = nullptr;
+    uint8_t* kind = nullptr; double4* params = nullptr;
+    // work buffers (grown on demand)
+    double* scratch = nullptr; size_t scratch_cap = 0;  // doubles
+    uint8_t* rgba = nullptr; size_t rgba_cap = 0;       // bytes
+    double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
+    unsigned long long* counters = nullptr; int counters_cap = 0;
+    unsigned long long* stats = nullptr;     // [0] segments [1] depth exhausted [2] progress samples
+    double* srgb_thr = nullptr;
+    uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+    // last render bookkeeping
+    std::vector<int> local_rows;  // global row of each local row
+    int passes = 0;
+};
+
+template <typename P>
+void grow(P*& ptr, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (ptr) CK(cudaFree(ptr));
+    ptr = nullptr; cap = 0;
+    CK(cudaMalloc(&ptr, need * sizeof(P)));
+    cap = need;
+}
+
+}  // namespace
+
+struct tray_ctx {
+    std::vector<Device> devs;
+    std::string err;
+    std::mutex mu;
+    bool have_scene = false;
+    double bg_a[3] = {1, 1, 1}, bg_b[3] = {0.4, 0.65, 1.0};
+    // last render
+    int width = 0, height = 0, y0 = 0, y1 = 0;
+    bool have_image = false, have_hdr = false;
+    int split_mode = 0;
+    std::atomic<uint64_t> progress_base{0};
+    std::atomic<int> progress_spp{1};
+    std::atomic<bool> rendering{false};
+    cudaStream_t peek_stream = nullptr;
+    unsigned long long* peek_host = nullptr;
+};
+
+namespace {
+
+int fail(tray_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_init_error = msg;
+    return code;
+}
+
+void free_scene(Device& d) {
+    cudaSetDevice(d.dev);
+    cudaFree(d.geo_d); cudaFree(d.geo_f); cudaFree(d.radius_d); cudaFree(d.radius_f); cudaFree(d.kind); cudaFree(d.params);
+    d.geo_d = nullptr; d.geo_f = nullptr; d.radius_d = nullptr; d.radius_f = nullptr; d.kind = nullptr; d.params = nullptr;
+}
+
+template <typename T> DevScene<T> dev_scene(const tray_ctx* ctx, const Device& d);
+template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device& d) {
+    DevScene<double> s;
+    s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
+    for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
+    return s;
+}
+template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& d) {
+    DevScene<float> s;
+    s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
+    for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
+    return s;
+}
+
+DevCamera dev_camera(const tray_camera* c) {
+    DevCamera d;
+    for (int i = 0; i < 3; i++) {
+        d.pos[i] = c->position[i]; d.p00[i] = c->pixel00[i]; d.px[i] = c->pixel_x[i]; d.py[i] = c->pixel_y[i];
+        d.du[i] = c->defocus_u[i]; d.dv[i] = c->defocus_v[i];
+    }
+    d.aperture = c->aperture; d.focus_distance = c->focus_distance; d.focal_length = c->focal_length;
+    return d;
+}
+
+constexpr int kTPB = 128;
+constexpr int kMinBlocks = 4;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+template <typename T, bool FMA>
+struct TraceLaunch {
+    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S) {
+        typedef typename Vec4T<T>::type T4;
+        size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
+        size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
+        bool smem_geo = geo_bytes + tail <= kSmemBudget;
+        size_t smem = (smem_geo ? geo_bytes : 0) + tail;
+        int bps = 0;
+        if (smem_geo) {
+            auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, true>;
+            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+            if (bps < 1) bps = 1;
+            k<<<d.num_sms * bps, kTPB, smem, d.stream>>>(A, S);
+        } else {
+            auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, false>;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+            if (bps < 1) bps = 1;
+            k<<<d.num_sms * bps, kTPB, smem, d.stream>>>(A, S);
+        }
+        CK(cudaGetLastError());
+    }
+};
+
+void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision) {
+    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d));
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d));
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d));
+}
+
+constexpr int kBandRows = 8;
+// Scratch budget per pass, in samples (x24 bytes). Whole pixels per pass.
+constexpr unsigned long long kPassSamples = 48ull << 20;
+
+}  // namespace
+
+extern "C" {
+
+int tray_abi_version(void) { return TRAY_ABI_VERSION; }
+
+const char* tray_last_error(tray_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int tray_init(const int* devices, int n_devices, tray_ctx** out) {
+    if (!out) return fail(nullptr, TRAY_E_INVALID, "tray_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, TRAY_E_NO_DEVICE, std::string("tray_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    std::vector<int> ids;
+    if (!devices || n_devices <= 0) ids.push_back(0);
+    else ids.assign(devices, devices + n_devices);
+    if (ids.size() > 8) return fail(nullptr, TRAY_E_INVALID, "tray_init: at most 8 devices per context");
+    tray_ctx* ctx = new tray_ctx();
+    try {
+        double thr[256];
+        build_srgb_thresholds(thr);
+        for (int id : ids) {
+            if (id < 0 || id >= count) throw std::runtime_error("tray_init: device index out of range");
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, id));
+            if (prop.major < 10) throw std::runtime_error(std::string("tray_init: device ") + prop.name + " is not sm_100 class; libtraycuda is built for sm_100a only");
+            Device d;
+            d.dev = id;
+            d.num_sms = prop.multiProcessorCount;
+            CK(cudaSetDevice(id));
+            CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&d.ev_begin)); CK(cudaEventCreate(&d.ev_trace_end)); CK(cudaEventCreate(&d.ev_end));
+            CK(cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)));
+            CK(cudaMemset(d.stats, 0, 8 * sizeof(unsigned long long)));
+            CK(cudaMalloc(&d.srgb_thr, 256 * sizeof(double)));
+            CK(cudaMemcpy(d.srgb_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
+            CK(cudaMemcpyToSymbol(g_zig_kn, ZIG_KN_INIT, sizeof(uint32_t) * 128));
+            CK(cudaMemcpyToSymbol(g_zig_wn, ZIG_WN_INIT, sizeof(float) * 128));
+            CK(cudaMemcpyToSymbol(g_zig_fn, ZIG_FN_INIT, sizeof(float) * 128));
+            ctx->devs.push_back(d);
+        }
+        // peer access for the sample-split combine (root reads peers' partial sums over NVLink)
+        for (size_t i = 1; i < ctx->devs.size(); i++) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[i].dev));
+            if (can) {
+                CK(cudaSetDevice(ctx->devs[0].dev));
+                cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->devs[i].dev, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                cudaGetLastError();
+            }
+        }
+        CK(cudaSetDevice(ctx->devs[0].dev));
+        CK(cudaStreamCreateWithFlags(&ctx->peek_stream, cudaStreamNonBlocking));
+        CK(cudaHostAlloc(&ctx->peek_host, sizeof(unsigned long long), cudaHostAllocDefault));
+    } catch (const std::exception& ex) {
+        g_init_error = ex.what();
+        tray_destroy(ctx);
+        return TRAY_E_CUDA;
+    }
+    *out = ctx;
+    return TRAY_OK;
+}
+
+void tray_destroy(tray_ctx* ctx) {
+    if (!ctx) return;
+    for (Device& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        cudaStreamSynchronize(d.stream);
+        free_scene(d);
+        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stats); cudaFree(d.srgb_thr);
+        if (d.pinned) cudaFreeHost(d.pinned);
+        if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+        if (d.ev_trace_end) cudaEventDestroy(d.ev_trace_end);
+        if (d.ev_end) cudaEventDestroy(d.ev_end);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (ctx->peek_stream) cudaStreamDestroy(ctx->peek_stream);
+    if (ctx->peek_host) cudaFreeHost(ctx->peek_host);
+    delete ctx;
+}
+
+int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!sc || sc->n < 0 || (sc->n > 0 && (!sc->cx || !sc->cy || !sc->cz || !sc->radius || !sc->mat_kind || !sc->mat_params)))
+        return fail(ctx, TRAY_E_INVALID, "tray_scene_upload: null array");
+    if (sc->n > 65535) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_scene_upload: more than 65535 spheres");
+    for (int i = 0; i < sc->n; i++)
+        if (sc->mat_kind[i] > TRAY_MAT_DIELECTRIC) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_scene_upload: unknown material kind (only Lambertian/Metal/Dielectric spheres are supported; no CPU fallback)");
+    try {
+        int n = sc->n, n_pad = std::max(4, (n + 3) / 4 * 4);
+        const double ninf = -std::numeric_limits<double>::infinity();
+        std::vector<double4> gd(n_pad); std::vector<float4> gf(n_pad);
+        std::vector<double> rd(n_pad, 1.0); std::vector<float> rf(n_pad, 1.0f);
+        std::vector<uint8_t> kd(n_pad, 0); std::vector<double4> pr(n_pad);
+        for (int i = 0; i < n_pad; i++) {
+            if (i < n) {
+                double r = sc->radius[i];
+                gd[i] = make_double4(sc->cx[i], sc->cy[i], sc->cz[i], r * r);  // Radius*Radius, objects.go:85
+                float fr = (float)r;
+                gf[i] = make_float4((float)sc->cx[i], (float)sc->cy[i], (float)sc->cz[i], fr * fr);
+                rd[i] = r; rf[i] = fr; kd[i] = sc->mat_kind[i];
+                pr[i] = make_double4(sc->mat_params[4 * i], sc->mat_params[4 * i + 1], sc->mat_params[4 * i + 2], sc->mat_params[4 * i + 3]);
+            } else {  // padding: c = +inf, disc = -inf -> certainly missed
+                gd[i] = make_double4(0, 0, 0, ninf);
+                gf[i] = make_float4(0, 0, 0, (float)ninf);
+                pr[i] = make_double4(0, 0, 0, 0);
+            }
+        }
+        for (Device& d : ctx->devs) {
+            CK(cudaSetDevice(d.dev));
+            CK(cudaStreamSynchronize(d.stream));
+            free_scene(d);
+            d.n = n; d.n_pad = n_pad;
+            CK(cudaMalloc(&d.geo_d, sizeof(double4) * n_pad)); CK(cudaMalloc(&d.geo_f, sizeof(float4) * n_pad));
+            CK(cudaMalloc(&d.radius_d, sizeof(double) * n_pad)); CK(cudaMalloc(&d.radius_f, sizeof(float) * n_pad));
+            CK(cudaMalloc(&d.kind, n_pad)); CK(cudaMalloc(&d.params, sizeof(double4) * n_pad));
+            CK(cudaMemcpy(d.geo_d, gd.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.geo_f, gf.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.radius_d, rd.data(), sizeof(double) * n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.radius_f, rf.data(), sizeof(float) * n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.kind, kd.data(), n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
+        }
+        for (int i = 0; i < 3; i++) { ctx->bg_a[i] = sc->bg_a[i]; ctx->bg_b[i] = sc->bg_b[i]; }
+        ctx->have_scene = true;
+    } catch (const std::exception& ex) {
+        return fail(ctx, TRAY_E_CUDA, ex.what());
+    }
+    return TRAY_OK;
+}
+
+static void copy_out(tray_ctx* ctx, uint8_t* rgba_out, size_t stride) {
+    // gather: every device's local rows -> pinned staging -> caller rows
+    const size_t row_bytes = (size_t)ctx->width * 4;
+    for (Device& d : ctx->devs) {
+        size_t nrows = d.local_rows.size();
+        if (!nrows) continue;
+        CK(cudaSetDevice(d.dev));
+        size_t bytes = nrows * row_bytes;
+        if (bytes > d.pinned_cap) {
+            if (d.pinned) CK(cudaFreeHost(d.pinned));
+            d.pinned = nullptr; d.pinned_cap = 0;
+            CK(cudaHostAlloc(&d.pinned, bytes, cudaHostAllocDefault));
+            d.pinned_cap = bytes;
+        }
+        CK(cudaMemcpyAsync(d.pinned, d.rgba, bytes, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (Device& d : ctx->devs) {
+        size_t nrows = d.local_rows.size();
+        if (!nrows) continue;
+        CK(cudaSetDevice(d.dev));
+        CK(cudaStreamSynchronize(d.stream));
+        size_t r = 0;
+        while (r < nrows) {  // coalesce runs of consecutive rows when the caller's stride is tight
+            size_t e = r + 1;
+            if (stride == row_bytes)
+                while (e < nrows && d.local_rows[e] == d.local_rows[e - 1] + 1) e++;
+            memcpy(rgba_out + (size_t)d.local_rows[r] * stride, d.pinned + r * row_bytes, (e - r) * row_bytes);
+            r = e;
+        }
+    }
+}
+
+int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uint8_t* rgba_out, size_t stride, tray_stats* stats) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!cam || !p) return fail(ctx, TRAY_E_INVALID, "tray_render: null camera/params");
+    if (!ctx->have_scene) return fail(ctx, TRAY_E_NO_SCENE, "tray_render: no scene uploaded");
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth <= 0)
+        return fail(ctx, TRAY_E_INVALID, "tray_render: width/height/spp/max_depth must be > 0 (apply Tracer defaults on the host)");
+    if (p->max_depth > kMaxDepth) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_render: max_depth > 256");
+    if (p->y0 < 0 || p->y1 > p->height || p->y0 > p->y1) return fail(ctx, TRAY_E_INVALID, "tray_render: bad row range");
+    if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
+    if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP32) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
+    if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
+    auto t_start = std::chrono::steady_clock::now();
+    const int rows = p->y1 - p->y0;
+    const int G = (int)ctx->devs.size();
+    int launches = 0;
+    try {
+        ctx->width = p->width; ctx->height = p->height; ctx->y0 = p->y0; ctx->y1 = p->y1;
+        ctx->have_image = false; ctx->have_hdr = false;
+        ctx->progress_base = 0; ctx->progress_spp = p->spp; ctx->rendering = true;
+        for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; }
+        DevCamera dcam = dev_camera(cam);
+        const int ext_count = p->shard_count > 1 ? p->shard_count : 1;
+        const int ext_index = p->shard_count > 1 ? p->shard_index : 0;
+        if (ext_index < 0 || ext_index >= ext_count) throw std::runtime_error("tray_render: shard_index out of range");
+
+        if (p->stream_mode == TRAY_STREAM_REFERENCE) {
+            // ---- conformance: reference chunk streams on device 0, one warp per chunk ----
+            if (p->precision == TRAY_FP32) throw std::runtime_error("tray_render: reference streams are fp64 only");
+            if (ctx->devs[0].n_pad * sizeof(double4) + sizeof(ZigTables) > kSmemBudget) throw std::runtime_error("tray_render: scene too large for the conformance kernel");
+            Device& d = ctx->devs[0];
+            CK(cudaSetDevice(d.dev));
+            RefArgs A;
+            A.cam = dcam; A.width = p->width; A.spp = p->spp; A.max_depth = p->max_depth; A.ray_radius = p->ray_radius;
+            A.seed = p->seed; A.row_begin = p->y0; A.row_end = p->y1;
+            if (p->num_workers <= 0 || p->stream_idx >= 0) {  // RenderLines(idx, y0, y1): one stream
+                A.chunk_rows = std::max(rows, 1); A.n_chunks = 1; A.idx_override = p->stream_idx >= 0 ? p->stream_idx : p->y0;
+            } else if (p->num_workers == 1) {                   // tracer.go:87-89
+                A.chunk_rows = std::max(rows, 1); A.n_chunks = 1; A.idx_override = 0;
+            } else {                                            // tracer.go:93-103
+                int chunk = std::max(4, p->height / (p->num_workers * 4));
+                A.chunk_rows = chunk; A.n_chunks = (rows + chunk - 1) / chunk; A.idx_override = -1;
+            }
+            size_t px = (size_t)rows * p->width;
+            grow(d.rgba, d.rgba_cap, std::max<size_t>(px * 4, 4));
+            grow(d.hdr, d.hdr_cap, std::max<size_t>(px * 3, 3));
+            A.rgba = d.rgba; A.hdr = d.hdr; A.srgb_thr = d.srgb_thr; A.stats = d.stats;
+            CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
+            CK(cudaEventRecord(d.ev_begin, d.stream));
+            if (rows > 0) {
+                size_t smem = (size_t)d.n_pad * sizeof(double4) + sizeof(ZigTables);
+                DevScene<double> S = dev_scene<double>(ctx, d);
+                if (p->precision == TRAY_FP64_FMA) {
+                    CK(cudaFuncSetAttribute(reference_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    reference_stream_kernel<true><<<A.n_chunks, 32, smem, d.stream>>>(A, S);
+                } else {
+                    CK(cudaFuncSetAttribute(reference_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    reference_stream_kernel<false><<<A.n_chunks, 32, smem, d.stream>>>(A, S);
+                }
+                CK(cudaGetLastError());
+                launches++;
+            }
+            CK(cudaEventRecord(d.ev_trace_end, d.stream));
+            CK(cudaEventRecord(d.ev_end, d.stream));
+            for (int r = 0; r < rows; r++) d.local_rows.push_back(p->y0 + r);
+        } else {
+            // ---- throughput mode: per-sample streams, persistent megakernel ----
+            const bool split_samples = (p->split_mode == TRAY_SPLIT_SAMPLES) && G > 1;
+            if (split_samples && ext_count > 1) throw std::runtime_error("tray_render: sample split cannot be combined with external shards");
+            for (int g = 0; g < G; g++) {
+                Device& d = ctx->devs[g];
+                CK(cudaSetDevice(d.dev));
+                // which rows does this device own?
+                int shard_count, shard_index;
+                if (split_samples) { shard_count = ext_count; shard_index = ext_index; }
+                else { shard_count = ext_count * G; shard_index = ext_index * G + g; }
+                for (int r = 0; r < rows; r++)
+                    if (shard_count <= 1 || (r / kBandRows) % shard_count == shard_index) d.local_rows.push_back(p->y0 + r);
+                const unsigned long long n_pixels = (unsigned long long)d.local_rows.size() * p->width;
+                int spp_local = p->spp, stride_s = 1, offset_s = 0;
+                if (split_samples) {
+                    stride_s = G; offset_s = g;
+                    spp_local = p->spp > g ? (p->spp - g + G - 1) / G : 0;
+                }
+                CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
+                grow(d.rgba, d.rgba_cap, std::max<size_t>(n_pixels * 4, 4));
+                grow(d.hdr, d.hdr_cap, std::max<size_t>(n_pixels * 3, 3));
+                CK(cudaEventRecord(d.ev_begin, d.stream));
+                if (n_pixels == 0 || spp_local == 0) {
+                    if (split_samples && n_pixels) CK(cudaMemsetAsync(d.hdr, 0, n_pixels * 3 * sizeof(double), d.stream));
+                    CK(cudaEventRecord(d.ev_trace_end, d.stream));
+                    CK(cudaEventRecord(d.ev_end, d.stream));
+                    continue;
+                }
+                unsigned long long px_per_pass = std::max<unsigned long long>(1, kPassSamples / (unsigned)spp_local);
+                px_per_pass = std::min(px_per_pass, n_pixels);
+                int n_pass = (int)((n_pixels + px_per_pass - 1) / px_per_pass);
+                grow(d.scratch, d.scratch_cap, (size_t)(px_per_pass * spp_local * 3));
+                if (n_pass > d.counters_cap) {
+                    if (d.counters) CK(cudaFree(d.counters));
+                    d.counters = nullptr;
+                    CK(cudaMalloc(&d.counters, sizeof(unsigned long long) * n_pass));
+                    d.counters_cap = n_pass;
+                }
+                CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * n_pass, d.stream));
+                d.passes = n_pass;
+                for (int ps = 0; ps < n_pass; ps++) {
+                    unsigned long long p0 = (unsigned long long)ps * px_per_pass;
+                    unsigned long long npx = std::min(px_per_pass, n_pixels - p0);
+                    TraceArgs A;
+                    A.cam = dcam; A.width = p->width; A.spp = p->spp; A.max_depth = p->max_depth;
+                    A.ray_radius = p->ray_radius; A.seed = p->seed;
+                    A.n_samples = npx * spp_local; A.pass_pixel0 = p0; A.row0 = p->y0;
+                    A.band_rows = kBandRows; A.shard_count = shard_count; A.shard_index = shard_index;
+                    A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
+                    A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
+                    launch_trace(ctx, d, A, p->precision);
+                    ResolveArgs R;
+                    R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
+                    R.inv_spp = 1.0 / (double)p->spp; R.partial = split_samples ? 1 : 0;
+                    R.rgba = d.rgba; R.hdr = d.hdr; R.srgb_thr = d.srgb_thr;
+                    resolve_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d.stream>>>(R);
+                    CK(cudaGetLastError());
+                    launches += 2;
+                }
+                CK(cudaEventRecord(d.ev_trace_end, d.stream));
+                CK(cudaEventRecord(d.ev_end, d.stream));
+            }
+            if (split_samples) {
+                // root sums the partial HDR sums of all devices through peer pointers, then sRGB: one kernel
+                for (int g = 1; g < G; g++) { CK(cudaSetDevice(ctx->devs[g].dev)); CK(cudaStreamSynchronize(ctx->devs[g].stream)); }
+                Device& d0 = ctx->devs[0];
+                CK(cudaSetDevice(d0.dev));
+                const unsigned long long n_pixels = (unsigned long long)d0.local_rows.size() * p->width;
+                CombineArgs C;
+                for (int g = 0; g < G; g++) C.partial[g] = ctx->devs[g].hdr;
+                C.n_parts = G; C.n_pixels = n_pixels; C.inv_spp = 1.0 / (double)p->spp;
+                C.rgba = d0.rgba; C.srgb_thr = d0.srgb_thr;
+                // combine in place is not possible (hdr is an input): reuse scratch for the mean
+                grow(d0.scratch, d0.scratch_cap, std::max<size_t>(n_pixels * 3, 3));
+                C.hdr = d0.scratch;
+                if (n_pixels) {
+                    combine_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, d0.stream>>>(C);
+                    CK(cudaGetLastError());
+                    CK(cudaMemcpyAsync(d0.hdr, d0.scratch, n_pixels * 3 * sizeof(double), cudaMemcpyDeviceToDevice, d0.stream));
+                    launches++;
+                }
+                CK(cudaEventRecord(d0.ev_end, d0.stream));
+                for (int g = 1; g < G; g++) ctx->devs[g].local_rows.clear();  // only the root holds the image
+            }
+        }
+        ctx->split_mode = p->split_mode;
+        if (rgba_out) copy_out(ctx, rgba_out, stride);
+        double kernel_ms = 0, trace_ms = 0;
+        unsigned long long seg = 0, exh = 0;
+        for (Device& d : ctx->devs) {
+            CK(cudaSetDevice(d.dev));
+            CK(cudaStreamSynchronize(d.stream));
+            float ms = 0, ms2 = 0;
+            CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+            CK(cudaEventElapsedTime(&ms2, d.ev_begin, d.ev_trace_end));
+            kernel_ms = std::max(kernel_ms, (double)ms);
+            trace_ms = std::max(trace_ms, (double)ms2);
+            unsigned long long st[3];
+            CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
+            seg += st[0]; exh += st[1];
+        }
+        ctx->have_image = true; ctx->have_hdr = true;
+        ctx->rendering = false;
+        unsigned long long my_rows = 0;
+        if (p->stream_mode == TRAY_STREAM_REFERENCE || (p->split_mode == TRAY_SPLIT_SAMPLES && G > 1)) {
+            for (int r = 0; r < rows; r++)
+                if (ext_count <= 1 || (r / kBandRows) % ext_count == ext_index || p->stream_mode == TRAY_STREAM_REFERENCE) my_rows++;
+        } else {
+            for (Device& d : ctx->devs) my_rows += d.local_rows.size();
+        }
+        ctx->progress_base = my_rows * (unsigned long long)p->width;
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            stats->paths = my_rows * (unsigned long long)p->width * (unsigned long long)p->spp;
+            stats->segments = seg;
+            stats->sphere_tests = seg * (unsigned long long)ctx->devs[0].n;
+            stats->depth_exhausted = exh;
+            stats->kernel_ms = kernel_ms;
+            stats->trace_kernel_ms = trace_ms;
+            stats->launches = launches;
+            stats->n_devices = G;
+            stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+        }
+    } catch (const std::exception& ex) {
+        ctx->rendering = false;
+        return fail(ctx, TRAY_E_CUDA, ex.what());
+    }
+    return TRAY_OK;
+}
+
+int tray_read_image(tray_ctx* ctx, uint8_t* rgba_out, size_t stride) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->have_image) return fail(ctx, TRAY_E_INVALID, "tray_read_image: nothing rendered");
+    if (!rgba_out || stride < (size_t)ctx->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_read_image: bad buffer");
+    try { copy_out(ctx, rgba_out, stride); } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+int tray_read_hdr(tray_ctx* ctx, double* hdr_out) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->have_hdr || !hdr_out) return fail(ctx, TRAY_E_INVALID, "tray_read_hdr: nothing rendered / null buffer");
+    try {
+        const size_t row_d = (size_t)ctx->width * 3;
+        std::vector<double> tmp;
+        for (Device& d : ctx->devs) {
+            size_t nrows = d.local_rows.size();
+            if (!nrows) continue;
+            CK(cudaSetDevice(d.dev));
+            tmp.resize(nrows * row_d);
+            CK(cudaMemcpy(tmp.data(), d.hdr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t r = 0; r < nrows; r++)
+                memcpy(hdr_out + (size_t)d.local_rows[r] * row_d, tmp.data() + r * row_d, row_d * sizeof(double));
+        }
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+int tray_first_hit(tray_ctx* ctx, const tray_camera* cam, int32_t width, int32_t height, int32_t precision,
+                   int32_t* id, double* t, double* normal, uint8_t* front) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!cam || !id || !t || !normal || !front || width <= 0 || height <= 0) return fail(ctx, TRAY_E_INVALID, "tray_first_hit: bad argument");
+    if (!ctx->have_scene) return fail(ctx, TRAY_E_NO_SCENE, "tray_first_hit: no scene uploaded");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        size_t n = (size_t)width * height;
+        int* d_id; double *d_t, *d_n; unsigned char* d_f;
+        CK(cudaMalloc(&d_id, n * 4)); CK(cudaMalloc(&d_t, n * 8)); CK(cudaMalloc(&d_n, n * 24)); CK(cudaMalloc(&d_f, n));
+        DevCamera dc = dev_camera(cam);
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (precision == TRAY_FP64_FMA) first_hit_kernel<double, true><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
+        else if (precision == TRAY_FP64_STRICT) first_hit_kernel<double, false><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
+        else first_hit_kernel<float, true><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<float>(ctx, d), width, height, d_id, d_t, d_n, d_f);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpy(id, d_id, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(t, d_t, n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(normal, d_n, n * 24, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(front, d_f, n, cudaMemcpyDeviceToHost));
+        cudaFree(d_id); cudaFree(d_t); cudaFree(d_n); cudaFree(d_f);
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+int tray_rng_dump(tray_ctx* ctx, int32_t kind, uint64_t idx, uint64_t seed, double radius, int32_t n, double* out) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!out || n <= 0 || kind < 0 || kind > 4) return fail(ctx, TRAY_E_INVALID, "tray_rng_dump: bad argument");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        int per = kind == 3 ? 3 : (kind == 4 ? 2 : 1);
+        double* dout;
+        CK(cudaMalloc(&dout, sizeof(double) * n * per));
+        rng_dump_kernel<<<1, 128, 0, d.stream>>>(kind, idx, seed, radius, n, dout);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpy(out, dout, sizeof(double) * n * per, cudaMemcpyDeviceToHost));
+        cudaFree(dout);
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+int tray_linear_to_srgb(tray_ctx* ctx, const double* x, int32_t n, uint8_t* out) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!x || !out || n <= 0) return fail(ctx, TRAY_E_INVALID, "tray_linear_to_srgb: bad argument");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        double* dx; unsigned char* dout;
+        CK(cudaMalloc(&dx, sizeof(double) * n)); CK(cudaMalloc(&dout, n));
+        CK(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+        srgb_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(dx, n, d.srgb_thr, dout);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpy(out, dout, n, cudaMemcpyDeviceToHost));
+        cudaFree(dx); cudaFree(dout);
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+uint64_t tray_progress(tray_ctx* ctx) {
+    if (!ctx) return 0;
+    if (!ctx->rendering.load()) return ctx->progress_base.load();
+    // render in flight (another thread holds ctx->mu): peek at the device counters on a side stream
+    uint64_t samples = 0;
+    for (Device& d : ctx->devs) {
+        if (cudaSetDevice(d.dev) != cudaSuccess) continue;
+        if (cudaMemcpyAsync(ctx->peek_host, d.stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->peek_stream) != cudaSuccess) continue;
+        if (cudaStreamSynchronize(ctx->peek_stream) != cudaSuccess) continue;
+        samples += *ctx->peek_host;
+    }
+    int spp = ctx->progress_spp.load();
+    return samples / (uint64_t)(spp > 0 ? spp : 1);
+}
+
+int tray_measure_peak(tray_ctx* ctx, int32_t kind, double* tflops, double* ms_out) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!tflops || kind < 0 || kind > 2) return fail(ctx, TRAY_E_INVALID, "tray_measure_peak: bad argument");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        double* sink;
+        CK(cudaMalloc(&sink, 8));
+        const int iters = 1 << 15, blocks = d.num_sms * 8, tpb = 256;
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(a, d.stream));
+            if (kind == 0) peak_kernel<0><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
+            else if (kind == 1) peak_kernel<1><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
+            else peak_kernel<2><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(b, d.stream));
+            CK(cudaStreamSynchronize(d.stream));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        // ops: every chain step is 2 flops (fma, or mul+add)
+        double flops = 2.0 * 8 * (double)iters * (double)blocks * tpb;
+        *tflops = flops / (best * 1e-3) / 1e12;
+        if (ms_out) *ms_out = best;
+        cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+}  // extern "C"

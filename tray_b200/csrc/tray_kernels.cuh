@@ -1,0 +1,488 @@
+// tray_kernels.cuh -- the sm_100a kernels of the tray hot path.
+//
+//  trace_kernel      persistent megakernel: one path per lane, brute-force closest hit over the
+//                    SoA sphere table staged in shared memory, deferred candidate resolution,
+//                    lane-level path regeneration from a warp-private pool fed by one global
+//                    atomic counter. Replaces the per-sample body of Tracer.RenderLines
+//                    (ray/tracer.go:133-143) and everything below it.
+//  resolve_kernel    in-order sample sum, *(1/N), sRGB, RGBA8 store (ray/tracer.go:143-152).
+//  reference_stream_kernel  conformance mode: one WARP per reference chunk, the chunk's single
+//                    sequential stream (ray/tracer.go:120-155), warp-cooperative intersection.
+//  first_hit_kernel  RNG-free parity probe of Scene.Hit.
+#pragma once
+#include "tray_device.cuh"
+
+namespace tray {
+
+constexpr int kMaxDepth = 256;   // attenuation-stack capacity (ids); tray_render rejects larger MaxDepth
+constexpr int kCand = 8;         // deferred candidates per lane before an in-loop flush
+constexpr int kBatch = 128;      // samples a warp takes from the global counter at a time
+constexpr unsigned kFull = 0xffffffffu;
+
+struct TraceArgs {
+    DevCamera cam;
+    int width, spp, max_depth;
+    double ray_radius;
+    unsigned long long seed;
+    // work mapping: local pixel lp -> (x, local row) -> global row
+    unsigned long long n_samples;    // samples in this pass
+    unsigned long long pass_pixel0;  // first local pixel of this pass
+    int row0;                        // params.y0
+    int band_rows, shard_count, shard_index;
+    int spp_local, sample_stride, sample_offset;  // sample-split: s = sample_offset + j*sample_stride
+    unsigned long long* counter;
+    double* scratch;                 // n_samples x 3 linear colours, [pixel][sample][rgb]
+    unsigned long long* stats;       // [0] segments  [1] depth exhausted
+    unsigned long long* progress;    // samples finished (for tray_progress), may be null
+};
+
+__device__ __forceinline__ int map_row(const TraceArgs& A, int ly) {
+    if (A.shard_count <= 1) return A.row0 + ly;
+    int band = ly / A.band_rows, within = ly - band * A.band_rows;
+    return A.row0 + (band * A.shard_count + A.shard_index) * A.band_rows + within;
+}
+
+template <typename T>
+__device__ __forceinline__ T t_inf();
+template <> __device__ __forceinline__ double t_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_float(0x7f800000); }
+
+// Resolve this lane's deferred candidates in index order with the reference's running-closest rule
+// (Scene.Hit, ray/objects.go:37-46): a later sphere wins only if strictly closer.
+template <typename T, bool FMA, int TPB>
+__device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type* geo, const uint16_t* cand, int ncand,
+                                                   T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
+    for (int k = 0; k < ncand; k++) {
+        int id = cand[k * TPB];
+        typename Vec4T<T>::type g = geo[id];
+        T h, c, disc, root;
+        sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+        if (sphere_root<T>(h, a, disc, T(1e-6), best_t, root)) { best_t = root; best = id; }
+    }
+}
+
+template <typename T, bool FMA, int TPB>
+__device__ __noinline__ void flush_candidates(const typename Vec4T<T>::type* geo, const uint16_t* cand, int ncand,
+                                              T ox, T oy, T oz, T dx, T dy, T dz, T a, T* best_t, int* best) {
+    T bt = *best_t; int b = *best;
+    resolve_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, bt, b);
+    *best_t = bt; *best = b;
+}
+
+template <typename T, bool FMA, int TPB, int MINB, bool SMEM_GEO>
+__global__ void __launch_bounds__(TPB, MINB) trace_kernel(const TraceArgs A, const DevScene<T> S) {
+    typedef typename Vec4T<T>::type T4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T4* sgeo = reinterpret_cast<T4*>(smem_raw);
+    const size_t geo_bytes = SMEM_GEO ? (size_t)S.n_pad * sizeof(T4) : 0;
+    ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
+    uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
+    const int tid = threadIdx.x;
+    if (SMEM_GEO)
+        for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
+    zig_load(zig, tid, TPB);
+    __syncthreads();
+    const T4* geo = SMEM_GEO ? sgeo : S.geo;
+    uint16_t* cand = cand_all + tid;  // this lane's list: cand[k*TPB]
+
+    const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool has = false, exhausted = false;
+    unsigned long long pool_next = 0, pool_end = 0, my_li = 0;
+    // Idle lanes carry a ray that certainly misses everything (every sphere is far behind it), so the
+    // hot loop needs no "has a path" test.
+    V3<T> O = mk<T>(T(0), T(1e18), T(0)), D = mk<T>(T(0), T(1), T(0));
+    Pcg rng = pcg_new_idx(0, 0);
+    int depth_left = 0, sp = 0;
+    uint16_t stk[kMaxDepth];
+    unsigned long long nseg = 0, nexh = 0, ndone = 0;
+    const int n_pad = S.n_pad;
+
+    for (;;) {
+        // ---------------- path regeneration (lane level) ----------------
+        if (!exhausted) {
+            unsigned need = __ballot_sync(kFull, !has);
+            while (need) {
+                if (pool_next >= pool_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)kBatch);
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base >= A.n_samples) { exhausted = true; break; }
+                    pool_next = base;
+                    pool_end = base + kBatch < A.n_samples ? base + kBatch : A.n_samples;
+                }
+                unsigned avail = (unsigned)(pool_end - pool_next);
+                unsigned rank = __popc(need & lt_mask);
+                if (!has && rank < avail) {
+                    my_li = pool_next + rank;
+                    // local sample -> pixel, sample number, global stream index
+                    unsigned long long lp = A.pass_pixel0 + my_li / (unsigned)A.spp_local;
+                    int j = (int)(my_li % (unsigned)A.spp_local);
+                    int s = A.sample_offset + j * A.sample_stride;
+                    int ly = (int)(lp / (unsigned)A.width);
+                    int x = (int)(lp - (unsigned long long)ly * (unsigned)A.width);
+                    int y = map_row(A, ly);
+                    unsigned long long idx = ((unsigned long long)y * (unsigned)A.width + (unsigned)x) * (unsigned)A.spp + (unsigned)s;
+                    rng = pcg_new_idx(idx, A.seed);
+                    double jx = 0.0, jy = 0.0;
+                    if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);  // ray/tracer.go:136-139
+                    V3<double> o64, d64;
+                    get_ray(A.cam, rng, (double)x, (double)y, jx, jy, o64, d64);
+                    O = mk<T>(T(o64.x), T(o64.y), T(o64.z));
+                    D = mk<T>(T(d64.x), T(d64.y), T(d64.z));
+                    depth_left = A.max_depth;
+                    sp = 0;
+                    has = true;
+                }
+                unsigned cnt = __popc(need);
+                pool_next += cnt < avail ? cnt : avail;
+                need = __ballot_sync(kFull, !has);
+            }
+        }
+        if (!__any_sync(kFull, has)) break;
+
+        // ---------------- Scene.Hit: brute force over all spheres ----------------
+        const T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
+        const T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
+        T best_t = t_inf<T>();
+        int best = -1, ncand = 0;
+#pragma unroll 1
+        for (int i = 0; i < n_pad; i += 4) {
+            // four independent tests (ILP for the FP64 pipe), one branch per group
+            int m[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                T4 g = geo[i + u];
+                T h, c, disc;
+                sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+                m[u] = miss_bits(h, c, disc);
+            }
+            if ((m[0] & m[1] & m[2] & m[3]) >= 0) {  // some sphere of the group may be hit (rare)
+                if (ncand > kCand - 4) {
+                    flush_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                    ncand = 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (m[u] >= 0) { cand[ncand * TPB] = (uint16_t)(i + u); ncand++; }
+            }
+        }
+        resolve_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+
+        // ---------------- RayColor step (ray/objects.go:49-62) ----------------
+        if (has) {
+            nseg++;
+            bool finish = false;
+            V3<T> col = mk<T>(T(0), T(0), T(0));
+            if (best < 0) {
+                col = background<T>(S.bg_a, S.bg_b, D);
+                finish = true;
+            } else {
+                T4 g = geo[best];
+                V3<T> P, N;
+                bool front;
+                hit_record<T>(O, D, best_t, mk<T>(g.x, g.y, g.z), S.radius[best], P, N, front);
+                int kind = S.kind[best];
+                double4 prm = S.params[best];
+                V3<T> O2, D2;
+                bool alb;
+                bool scattered = scatter<T>(kind, prm, rng, zig, D, P, N, front, O2, D2, alb);
+                if (!scattered) {
+                    finish = true;  // absorbed: black
+                } else {
+                    if (alb) stk[sp++] = (uint16_t)best;
+                    O = O2; D = D2;
+                    depth_left--;
+                    if (depth_left <= 0) { finish = true; nexh++; }  // RayColor(depth<=0) = black
+                }
+            }
+            if (finish) {
+                if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
+                    for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56
+                        double4 prm = S.params[stk[k]];
+                        col = vmul(mk<T>(T(prm.x), T(prm.y), T(prm.z)), col);
+                    }
+                }
+                double* out = A.scratch + 3ull * my_li;
+                out[0] = (double)col.x; out[1] = (double)col.y; out[2] = (double)col.z;
+                has = false;
+                O = mk<T>(T(0), T(1e18), T(0)); D = mk<T>(T(0), T(1), T(0));
+                ndone++;
+            }
+        }
+    }
+
+    // stats: warp-reduce, one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        nseg += __shfl_down_sync(kFull, nseg, off);
+        nexh += __shfl_down_sync(kFull, nexh, off);
+        ndone += __shfl_down_sync(kFull, ndone, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&A.stats[0], nseg);
+        atomicAdd(&A.stats[1], nexh);
+        if (A.progress) atomicAdd(A.progress, ndone);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ResolveArgs {
+    const double* scratch;
+    unsigned long long n_pixels;      // pixels in this pass
+    unsigned long long pass_pixel0;   // first local pixel
+    int spp_local;
+    double inv_spp;                   // 1.0 / float64(NumRaysPerPixel), ray/tracer.go:123
+    int partial;                      // 1: store the raw partial sum only (sample-split)
+    unsigned char* rgba;              // local image, 4 B/pixel
+    double* hdr;                      // local, 3 doubles/pixel (mean, or partial sum when partial)
+    const double* srgb_thr;
+};
+
+__global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs R) {
+    unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= R.n_pixels) return;
+    const double* s = R.scratch + 3ull * p * (unsigned)R.spp_local;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int j = 0; j < R.spp_local; j++) {  // colorSum = Add(colorSum, color), sample order
+        sx = sx + s[3 * j];
+        sy = sy + s[3 * j + 1];
+        sz = sz + s[3 * j + 2];
+    }
+    unsigned long long lp = R.pass_pixel0 + p;
+    if (R.partial) {
+        R.hdr[3 * lp] = sx; R.hdr[3 * lp + 1] = sy; R.hdr[3 * lp + 2] = sz;
+        return;
+    }
+    double cx = sx * R.inv_spp, cy = sy * R.inv_spp, cz = sz * R.inv_spp;  // SMul(colorSum, colorSumDiv)
+    if (R.hdr) { R.hdr[3 * lp] = cx; R.hdr[3 * lp + 1] = cy; R.hdr[3 * lp + 2] = cz; }
+    uchar4 px;
+    px.x = linear_to_srgb(R.srgb_thr, cx);
+    px.y = linear_to_srgb(R.srgb_thr, cy);
+    px.z = linear_to_srgb(R.srgb_thr, cz);
+    px.w = 255;
+    reinterpret_cast<uchar4*>(R.rgba)[lp] = px;
+}
+
+// Sample-split epilogue: sum the per-device partial sums (peer pointers over NVLink, device order),
+// scale, convert and store -- the reduction and the sRGB store are one kernel.
+struct CombineArgs {
+    const double* partial[8];
+    int n_parts;
+    unsigned long long n_pixels;
+    double inv_spp;
+    unsigned char* rgba;
+    double* hdr;
+    const double* srgb_thr;
+};
+
+__global__ void __launch_bounds__(256) combine_kernel(const CombineArgs C) {
+    unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= C.n_pixels) return;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int g = 0; g < C.n_parts; g++) {
+        const double* q = C.partial[g] + 3 * p;
+        sx = sx + q[0]; sy = sy + q[1]; sz = sz + q[2];
+    }
+    double cx = sx * C.inv_spp, cy = sy * C.inv_spp, cz = sz * C.inv_spp;
+    if (C.hdr) { C.hdr[3 * p] = cx; C.hdr[3 * p + 1] = cy; C.hdr[3 * p + 2] = cz; }
+    uchar4 px;
+    px.x = linear_to_srgb(C.srgb_thr, cx);
+    px.y = linear_to_srgb(C.srgb_thr, cy);
+    px.z = linear_to_srgb(C.srgb_thr, cz);
+    px.w = 255;
+    reinterpret_cast<uchar4*>(C.rgba)[p] = px;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conformance mode: the reference's own stream semantics. One warp per chunk; all 32 lanes carry the
+// same path state and RNG (uniform, redundant), and split the sphere loop 32 ways.
+// ---------------------------------------------------------------------------------------------
+struct RefArgs {
+    DevCamera cam;
+    int width, spp, max_depth;
+    double ray_radius;
+    unsigned long long seed;
+    int row_begin, row_end;  // rows covered by all chunks
+    int chunk_rows, n_chunks;
+    long long idx_override;  // >= 0: the single chunk uses this stream index (RenderLines(idx,..)); else idx = chunk start row
+    unsigned char* rgba;     // local image covering rows [row_begin,row_end)
+    double* hdr;
+    const double* srgb_thr;
+    unsigned long long* stats;
+};
+
+template <bool FMA>
+__global__ void __launch_bounds__(32) reference_stream_kernel(const RefArgs A, const DevScene<double> S) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double4* geo = reinterpret_cast<double4*>(smem_raw);
+    ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + (size_t)S.n_pad * sizeof(double4));
+    const int lane = threadIdx.x;
+    for (int i = lane; i < S.n_pad; i += 32) geo[i] = S.geo[i];
+    zig_load(zig, lane, 32);
+    __syncwarp();
+    const int chunk = blockIdx.x;
+    if (chunk >= A.n_chunks) return;
+    const int ys = A.row_begin + chunk * A.chunk_rows;
+    const int ye = ys + A.chunk_rows < A.row_end ? ys + A.chunk_rows : A.row_end;
+    Pcg rng = pcg_new_idx(A.idx_override >= 0 ? (unsigned long long)A.idx_override : (unsigned long long)(long long)ys, A.seed);
+    const double inv_spp = 1.0 / (double)A.spp;
+    uint16_t stk[kMaxDepth];
+    unsigned long long nseg = 0, nexh = 0;
+    const double inf = t_inf<double>();
+
+    for (int y = ys; y < ye; y++) {
+        for (int x = 0; x < A.width; x++) {
+            V3<double> sum = mk<double>(0.0, 0.0, 0.0);
+            for (int s = 0; s < A.spp; s++) {
+                double jx = 0.0, jy = 0.0;
+                if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);
+                V3<double> O, D;
+                get_ray(A.cam, rng, (double)x, (double)y, jx, jy, O, D);
+                int depth_left = A.max_depth, sp = 0;
+                V3<double> col = mk<double>(0.0, 0.0, 0.0);
+                for (;;) {
+                    // cooperative Scene.Hit: lane l scans spheres l, l+32, ... with the running-closest rule,
+                    // then a lexicographic (t, id) warp minimum restores "ties -> lowest index".
+                    const double a = len2(D);
+                    double bt = inf;
+                    int b = -1;
+                    for (int i = lane; i < S.n; i += 32) {
+                        double4 g = geo[i];
+                        double h, c, disc, root;
+                        sphere_terms<double, FMA>(O.x, O.y, O.z, D.x, D.y, D.z, a, g.x, g.y, g.z, g.w, h, c, disc);
+                        if (sphere_root<double>(h, a, disc, 1e-6, bt, root)) { bt = root; b = i; }
+                    }
+                    for (int off = 16; off > 0; off >>= 1) {
+                        double ot = __shfl_xor_sync(kFull, bt, off);
+                        int ob = __shfl_xor_sync(kFull, b, off);
+                        if (ob >= 0 && (b < 0 || ot < bt || (ot == bt && ob < b))) { bt = ot; b = ob; }
+                    }
+                    nseg++;
+                    if (b < 0) { col = background<double>(S.bg_a, S.bg_b, D); break; }
+                    double4 g = geo[b];
+                    V3<double> P, N, O2, D2;
+                    bool front, alb;
+                    hit_record<double>(O, D, bt, mk<double>(g.x, g.y, g.z), S.radius[b], P, N, front);
+                    bool scattered = scatter<double>(S.kind[b], S.params[b], rng, zig, D, P, N, front, O2, D2, alb);
+                    if (!scattered) break;
+                    if (alb) stk[sp++] = (uint16_t)b;
+                    O = O2; D = D2;
+                    if (--depth_left <= 0) { nexh++; break; }
+                }
+                if (col.x != 0.0 || col.y != 0.0 || col.z != 0.0)
+                    for (int k = sp - 1; k >= 0; k--) {
+                        double4 prm = S.params[stk[k]];
+                        col = vmul(mk<double>(prm.x, prm.y, prm.z), col);
+                    }
+                sum = sum + col;
+            }
+            if (lane == 0) {
+                V3<double> c = sum * inv_spp;
+                size_t lp = (size_t)(y - A.row_begin) * A.width + x;
+                if (A.hdr) { A.hdr[3 * lp] = c.x; A.hdr[3 * lp + 1] = c.y; A.hdr[3 * lp + 2] = c.z; }
+                uchar4 px;
+                px.x = linear_to_srgb(A.srgb_thr, c.x);
+                px.y = linear_to_srgb(A.srgb_thr, c.y);
+                px.z = linear_to_srgb(A.srgb_thr, c.z);
+                px.w = 255;
+                reinterpret_cast<uchar4*>(A.rgba)[lp] = px;
+            }
+        }
+    }
+    if (lane == 0) { atomicAdd(&A.stats[0], nseg); atomicAdd(&A.stats[1], nexh); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RNG-free parity probe: Scene.Hit for the pixel-centre pinhole primary ray of every pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool FMA>
+__global__ void __launch_bounds__(128) first_hit_kernel(DevCamera cam, DevScene<T> S, int width, int height,
+                                                        int* id, double* t, double* normal, unsigned char* front) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= width * height) return;
+    int y = p / width, x = p - y * width;
+    cam.aperture = 0.0;
+    Pcg dummy = pcg_new_idx(0, 0);
+    V3<double> o64, d64;
+    get_ray(cam, dummy, (double)x, (double)y, 0.0, 0.0, o64, d64);
+    V3<T> O = mk<T>(T(o64.x), T(o64.y), T(o64.z)), D = mk<T>(T(d64.x), T(d64.y), T(d64.z));
+    T a = len2(D), bt = t_inf<T>();
+    int b = -1;
+    for (int i = 0; i < S.n; i++) {
+        typename Vec4T<T>::type g = S.geo[i];
+        T h, c, disc, root;
+        sphere_terms<T, FMA>(O.x, O.y, O.z, D.x, D.y, D.z, a, g.x, g.y, g.z, g.w, h, c, disc);
+        if (sphere_root<T>(h, a, disc, T(1e-6), bt, root)) { bt = root; b = i; }
+    }
+    id[p] = b;
+    t[p] = (double)bt;
+    if (b >= 0) {
+        typename Vec4T<T>::type g = S.geo[b];
+        V3<T> P, N;
+        bool ff;
+        hit_record<T>(O, D, bt, mk<T>(g.x, g.y, g.z), S.radius[b], P, N, ff);
+        normal[3 * p] = (double)N.x; normal[3 * p + 1] = (double)N.y; normal[3 * p + 2] = (double)N.z;
+        front[p] = ff ? 1 : 0;
+    } else {
+        normal[3 * p] = normal[3 * p + 1] = normal[3 * p + 2] = 0.0;
+        front[p] = 0;
+    }
+}
+
+// Generator parity probe (single thread).
+__global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long long seed, double radius, int n, double* out) {
+    __shared__ ZigTables zig;
+    zig_load(&zig, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Pcg r = pcg_new_idx(idx, seed);
+    for (int i = 0; i < n; i++) {
+        if (kind == 0) out[i] = __longlong_as_double((long long)pcg_u64(r));
+        else if (kind == 1) out[i] = pcg_f64(r);
+        else if (kind == 2) out[i] = pcg_norm(r, &zig);
+        else if (kind == 3) { V3<double> v = pcg_unit_vector(r, &zig); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+        else { double x, y; pcg_in_disc(r, radius, x, y); out[2 * i] = x; out[2 * i + 1] = y; }
+    }
+}
+
+__global__ void srgb_kernel(const double* x, int n, const double* thr, unsigned char* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = linear_to_srgb(thr, x[i]);
+}
+
+// Issue-bound pipe peaks (roofline denominators): 8 independent chains per thread.
+template <int KIND>
+__global__ void __launch_bounds__(256) peak_kernel(double* sink, int iters, double seedv) {
+    if (KIND == 2) {
+        float acc[8];
+        float m = 1.0000001f, b = (float)seedv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = (float)(threadIdx.x + k);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = fmaf(acc[k], m, b);
+        }
+        float s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += acc[k];
+        if (s == 12345.678f) sink[0] = s;
+    } else {
+        double acc[8];
+        double m = 1.0000000001, b = seedv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = (double)(threadIdx.x + k);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (KIND == 0) acc[k] = fma(acc[k], m, b);
+                else acc[k] = acc[k] * m + b;  // -fmad=false: one DMUL + one DADD
+            }
+        }
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += acc[k];
+        if (s == 12345.678) sink[0] = s;
+    }
+}
+
+}  // namespace tray
