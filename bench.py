@@ -1,0 +1,402 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the tray path-tracing hot path on B200 (Mpaths/s), driver contract.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # own arm, 1 GPU
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N GPUs, tile sharding
+    python bench.py --impl reference ...                               # reference arm: CPU port on host cores
+
+A "step" is one full render of the workload (one pass of the hot path over every pixel x sample).
+N=1 workload: BASELINE.json configs[1] (RichScene seed 2, 1920x1080, 64 rays/pixel, depth 50, fp64).
+N>1 workload: configs[2] (3840x2160, 256 rays/pixel, depth 50), interleaved 8-row bands across ranks,
+no data-path collective (each rank writes its own rows of the shared host image).
+
+Timed regions:
+  value  -- device-resident: scene already in HBM, image left in HBM; CUDA events recorded by the library
+            on its launch stream around each step's kernels, summed over K steps, MAX over ranks.
+  e2e    -- the reference-facing call sequence with HOST buffers every step: tray_scene_upload (H2D of the
+            flattened scene) + tray_render into a host RGBA buffer (D2H inside the call); wall clock
+            bracketed by synchronize + barrier, MAX over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (width, height, spp, depth, grid half-width, description)
+    "config1": (400, 225, 10, 50, 11, "benchmark scene seed 2, 400x225, 10 rays/pixel, depth 50"),
+    "config2": (1920, 1080, 64, 50, 11, "benchmark scene seed 2, 1920x1080, 64 rays/pixel, depth 50"),
+    "config3": (3840, 2160, 256, 50, 11, "benchmark scene seed 2, 3840x2160, 256 rays/pixel, depth 50"),
+    "config4": (1920, 1080, 64, 12, 50, "synthetic dense scene (~10k spheres), 1920x1080, 64 rays/pixel, depth 12"),
+    "config5": (640, 360, 64, 12, 11, "interactive tray path: 160x45 terminal, -s 4 -> 640x360, 64 rays/pixel, depth 12"),
+}
+SEED = 2
+FLOPS_PER_TEST = 18.0     # miss path of Sphere.Hit, `a` hoisted
+FLOPS_PER_SEGMENT = 155.0  # a = D.D (5) + closest-hit finish, scatter / sky, RNG fp (150)
+
+
+def algorithmic_flops(segments, n_spheres):
+    return float(segments) * (FLOPS_PER_TEST * n_spheres + FLOPS_PER_SEGMENT)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one trace_kernel launch from the committed `ncu --set full`
+    capture (profiles/, same command line); None when no capture is committed."""
+    import csv, glob
+    files = sorted(glob.glob(os.path.join(_ROOT, "profiles", "r*_trace_kernel_metrics.csv")))
+    if not files:
+        return None, None
+    tot, first = 0.0, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for r in csv.DictReader(open(files[-1])):
+        first = first if first is not None else r["launch_id"]
+        if r["launch_id"] == first and r["metric"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r["value"]) * scale.get(r["unit"], 1.0)
+    return (tot or None), os.path.basename(files[-1])
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port_run(workload, threads, target_seconds, fma_mode=0):
+    """Times the oracle (a C port of the reference's CPU loop) on a bounded sample of the workload:
+    rows y == 0 (mod step) of the image, per-sample streams, all host threads."""
+    from oracle import oracle as O
+    w, h, spp, depth, half, _ = WORKLOADS[workload]
+    scene = O.rich_scene(SEED, half)
+    cam = O.camera_init(w, h, **O.RICH_CAMERA)
+    p = O.make_params(w, h, spp=spp, max_depth=depth, seed=SEED, num_workers=threads, stream_mode=1, fma_mode=fma_mode)
+    # calibrate on a few rows spread over the image, then size the sample for ~target_seconds
+    cal_step = max(1, h // 4)
+    t0 = time.perf_counter()
+    _, st = O.render_sampled_rows(scene, cam, p, cal_step, cal_step // 2, threads)
+    dt = time.perf_counter() - t0
+    rate = st["paths"] / max(dt, 1e-6)
+    rows = int(max(threads, min(h, target_seconds * rate / (w * spp))))
+    step = max(1, h // rows)
+    return dict(scene=scene, cam=cam, params=p, step=step, threads=threads, rows=len(range(0, h, step)), O=O, w=w, h=h, spp=spp)
+
+
+def cpu_port_step(cp):
+    O = cp["O"]
+    t0 = time.perf_counter()
+    img, st = O.render_sampled_rows(cp["scene"], cp["cam"], cp["params"], cp["step"], 0, cp["threads"])
+    dt = time.perf_counter() - t0
+    return img, st, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (oracle port; Go cannot be built here) on all host
+    threads, same metric/config, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workload = args.workload or ("config2" if args.gpus == 1 else "config3")
+    threads = host_threads()
+    total_budget = 150.0
+    per_step = max(2.0, min(25.0, total_budget / max(1, args.steps + args.warmup)))
+    cp = cpu_port_run(workload, threads, per_step)
+    for _ in range(args.warmup):
+        cpu_port_step(cp)
+    paths, segs, secs = 0, 0, 0.0
+    for _ in range(args.steps):
+        _, st, dt = cpu_port_step(cp)
+        paths += st["paths"]; segs += st["segments"]; secs += dt
+    w, h, spp, depth, half, desc = WORKLOADS[workload]
+    val = paths / secs / 1e6
+    sample = "rows y%%%d==0 of %s (%d rows, %.2f Mpaths/step), per-sample streams, strict fp64 (Go/amd64 semantics)" % (
+        cp["step"], workload, cp["rows"], paths / args.steps / 1e6)
+    line = {"impl": "reference", "metric": "Mpaths/s", "value": val, "unit": "Mpaths/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "mrays_per_s": segs / secs / 1e6,
+            "config": {"workload": workload, "desc": desc, "width": w, "height": h, "rays_per_pixel": spp, "max_depth": depth,
+                       "seed": SEED, "spheres": cp["scene"].n},
+            "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "Go toolchain absent: the reference arm is the C oracle port of ray/tracer.go's loop on all host threads"}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tray_b200 import ray, rand, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; tray_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    workload = args.workload or ("config2" if args.gpus == 1 else "config3")
+    w, h, spp, depth, half, desc = WORKLOADS[workload]
+    PREC = {"fp64": ray.FP64_STRICT, "fp64-fma": ray.FP64_FMA, "fp32": ray.FP32}
+    precision = PREC[args.precision]
+
+    ctx = ray.Context([local_rank])
+    scene = ray.RichScene(rand.New(SEED), half)
+    tr = ray.New(w, h)
+    tr.Camera = ray.RichSceneCamera()
+    tr.MaxDepth, tr.NumRaysPerPixel, tr.Seed, tr.Precision = depth, spp, SEED, precision
+    tr.ShardIndex, tr.ShardCount = (rank, world) if world > 1 else (0, 0)
+    tr.Context = ctx
+    tr._prepare(scene)  # Tracer.Render's defaulting: default background, Camera.Initialize (ray/tracer.go:49-83)
+    flat = scene.flatten()
+    n_spheres = len(flat["cx"])
+    ctx.upload(flat)
+    cam_c = tr.to_c()
+    params = tr._params(0, h)
+
+    # shared host image for the e2e leg (each rank writes its own row bands; no collective)
+    if world > 1:
+        shm = "/dev/shm/tray_bench_%s.rgba" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            np.lib.format.open_memmap(shm, mode="w+", dtype=np.uint8, shape=(h, w, 4)).flush()
+        dist.barrier()
+        host_img = np.load(shm, mmap_mode="r+")
+    else:
+        host_img = np.zeros((h, w, 4), dtype=np.uint8)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peak_tf, _ = ctx.measure_peak(0)  # DFMA issue-bound peak of this GPU, measured live
+    peak_strict_tf, _ = ctx.measure_peak(1)
+    peak_f32_tf, _ = ctx.measure_peak(2)
+
+    # ---- device-resident leg ----
+    for _ in range(max(args.warmup, 3)):  # timing rules: at least 3 warm-up steps
+        ctx.render(cam_c, params, None)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms, trace_ms, launches, segments, paths, trace_launches = 0.0, 0.0, 0, 0, 0, 0
+    for _ in range(args.steps):
+        flush_buf.zero_()  # L2 flush between timed iterations (outside the event-timed kernels)
+        torch.cuda.synchronize()
+        st = ctx.render(cam_c, params, None)
+        dev_ms += st["kernel_ms"]; trace_ms += st["trace_kernel_ms"]; launches += st["launches"]
+        segments += st["segments"]; paths += st["paths"]; trace_launches += st["launches"] // 2
+    sync_all()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop()
+    dev_ms = max_over_ranks(dev_ms)
+    all_paths = sum_over_ranks(paths)
+    all_segments = sum_over_ranks(segments)
+    value = all_paths / (dev_ms * 1e-3) / 1e6
+    # roofline of the dominant kernel (trace_kernel) on this rank
+    flops = algorithmic_flops(segments, n_spheres)
+    achieved_tf = flops / (trace_ms * 1e-3) / 1e12 if trace_ms > 0 else 0.0
+    peak_used = {"fp64": peak_tf, "fp64-fma": peak_tf, "fp32": peak_f32_tf}[args.precision]
+    loop_probe_tf = ctx.measure_peak({"fp64": 4, "fp64-fma": 3, "fp32": 3}[args.precision])[0]
+
+    # ---- the opt-in fused-arithmetic mode, reported beside the default (same steps, device-resident) ----
+    alt = None
+    if args.precision == "fp64" and not args.no_alt:
+        p2 = tr._params(0, h)
+        p2.precision = ray.FP64_FMA
+        for _ in range(2):
+            ctx.render(cam_c, p2, None)
+        a_ms, a_trace, a_seg, a_paths = 0.0, 0.0, 0, 0
+        for _ in range(args.steps):
+            st2 = ctx.render(cam_c, p2, None)
+            a_ms += st2["kernel_ms"]; a_trace += st2["trace_kernel_ms"]; a_seg += st2["segments"]; a_paths += st2["paths"]
+        a_ms = max_over_ranks(a_ms)
+        a_tf = algorithmic_flops(a_seg, n_spheres) / (a_trace * 1e-3) / 1e12
+        alt = {"precision": "fp64-fma", "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+               "roofline_achieved_tflops": a_tf, "roofline_frac": a_tf / peak_tf,
+               "note": "Sphere.Hit discriminant with fused multiply-add (11 instead of 17 FP64 ops/test); image identical at 8 bits, "
+                       "first-hit ids exact, t within 1e-12, normals within 4e-11 of the strict result"}
+
+    # ---- end-to-end leg: host buffers, scene H2D + image D2H inside the timed region ----
+    for _ in range(min(args.warmup, 2)):
+        ctx.upload(flat); ctx.render(cam_c, params, host_img)
+    sync_all()
+    t0 = time.perf_counter()
+    e_paths = 0
+    for _ in range(args.steps):
+        ctx.upload(flat)
+        st = ctx.render(cam_c, params, host_img)
+        e_paths += st["paths"]
+    sync_all()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = sum_over_ranks(e_paths) / (e2e_ms * 1e-3) / 1e6
+    h2d = sum(flat[k].nbytes for k in ("cx", "cy", "cz", "r", "kind", "params")) + 48 + \
+        __import__("ctypes").sizeof(_lib.CameraC) + __import__("ctypes").sizeof(_lib.Params)
+    my_rows = st["paths"] // (w * spp)
+    d2h = int(my_rows * w * 4)
+
+    # ---- CPU baseline + parity spot check (rank 0, N=1 only) ----
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        cp = cpu_port_run(workload, threads, args.cpu_seconds, fma_mode=0)
+        img, cst, cdt = cpu_port_step(cp)
+        sample = "rows y%%%d==0 of %s (%d rows, %.2f Mpaths), per-sample streams, strict fp64, %.1f s" % (
+            cp["step"], workload, cp["rows"], cst["paths"] / 1e6, cdt)
+        cpu_baseline = {"value": cst["paths"] / cdt / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port", "sample": sample}
+        rows = list(range(0, h, cp["step"]))
+        d = np.abs(img[rows, :, :3].astype(np.int16) - host_img[rows, :, :3].astype(np.int16)).max(axis=2)
+        parity = {"rows_checked": len(rows), "pixels_identical_frac": float((d == 0).mean()), "pixels_within_1lsb_frac": float((d <= 1).mean()),
+                  "mode": "GPU %s vs strict CPU port (oracle)" % args.precision}
+
+    if rank == 0:
+        traffic, traffic_src = ncu_traffic_bytes() if workload == "config2" and args.precision == "fp64" else (None, None)
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": {"fp64": "f64", "fp64-fma": "f64", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "mrays_per_s": all_segments / (dev_ms * 1e-3) / 1e6,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "config": {"workload": workload, "desc": desc, "width": w, "height": h, "rays_per_pixel": spp, "max_depth": depth,
+                       "seed": SEED, "spheres": n_spheres, "precision": args.precision, "streams": "per-sample",
+                       "parallelism": "tiles%d" % world if world > 1 else "1gpu",
+                       "l2": "256 MiB memset between timed steps (L2 flush); working set is 31 kB of spheres in shared memory"},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "power_w_max": clocks.get("power_w_max"), "samples": clocks["samples"]},
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_used, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_used if peak_used else None, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per trace_kernel launch from %s (ncu --set full); algorithmic DRAM bytes are 24 B/path "
+                                         "of scratch written + read back by the resolve kernel" % traffic_src if traffic else None,
+                         "kernel": "tray::trace_kernel", "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(1, trace_launches),
+                         "algorithmic_flops_per_launch": flops / max(1, trace_launches),
+                         "flops_model": "segments*(18*N+155), N=%d spheres (SURVEY 8d)" % n_spheres,
+                         "peak_source": "measured live on this GPU by tray_measure_peak (DFMA chains, 8/thread); MEASURED_PEAKS.json has no fp64 entry",
+                         "peak_dadd_dmul_tflops": peak_strict_tf, "peak_ffma_tflops": peak_f32_tf,
+                         "loop_only_probe_tflops": loop_probe_tf,
+                         "structural_ceiling_frac": {"fp64": 18.0 / 34.0, "fp64-fma": 18.0 / 22.0, "fp32": 18.0 / 22.0}[args.precision],
+                         "note": "compute-bound on the FP64 pipe: HBM traffic is ~30 B/path of scratch; tensor cores do not apply"},
+            "segments_per_path": all_segments / all_paths,
+        }
+        if alt:
+            line["alt_modes"] = [alt]
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if parity:
+            line["parity_spot_check"] = parity
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm)
+            except OSError:
+                pass
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp64-fma", "fp32"],
+                    help="fp64 = strict Go/amd64 semantics (default); fp64-fma = fused discriminant; fp32 = fast path")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -71,6 +71,8 @@ def lib():
         _lib.oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib.oracle_render_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        _lib.oracle_render_sampled_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib.oracle_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
         _lib.oracle_camera_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.oracle_rng_u64.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -174,6 +176,20 @@ def render_lines(scene, cam, params, idx, y0, y1, rgba, hdr=None):
     lib().oracle_render_lines(C.byref(sc), C.byref(cam), C.byref(params), idx, y0, y1, _p(rgba), params.width * 4,
                               _p(hdr) if hdr is not None else None, C.byref(st))
     return st.as_dict()
+
+
+def render_sampled_rows(scene, cam, params, row_step, row_offset, threads, rgba=None):
+    """Rows y == row_offset (mod row_step) with per-sample streams on `threads` OS threads (bounded CPU baseline)."""
+    h, w = params.height, params.width
+    if rgba is None:
+        rgba = np.zeros((h, w, 4), dtype=np.uint8)
+    st = Stats()
+    sc = scene.c()
+    rc = lib().oracle_render_sampled_rows(C.byref(sc), C.byref(cam), C.byref(params), row_step, row_offset, threads,
+                                          _p(rgba), w * 4, None, C.byref(st))
+    if rc != 0:
+        raise RuntimeError("oracle_render_sampled_rows failed")
+    return rgba, st.as_dict()
 
 
 def first_hit(scene, cam, width, height, fma_mode=0):

@@ -572,6 +572,44 @@ EXPORT int oracle_render(const oracle_scene *sc, const oracle_camera *cam, const
     return 0;
 }
 
+/* Bounded CPU-baseline sample: rows y == row_offset (mod row_step), per-sample streams, `threads`
+ * OS threads pulling rows from a shared counter (same work-queue shape as ray/tracer.go:93-115). */
+typedef struct { const job_t *job; int step, next, height; pthread_mutex_t mu; oracle_stats st; } spool_t;
+static void *sample_worker(void *arg) {
+    spool_t *pl = (spool_t *)arg;
+    oracle_stats st = {0, 0, 0, 0, 0};
+    for (;;) {
+        pthread_mutex_lock(&pl->mu);
+        int y = pl->next;
+        pl->next += pl->step;
+        pthread_mutex_unlock(&pl->mu);
+        if (y >= pl->height) break;
+        render_rows_per_sample(pl->job, y, y + 1, &st);
+    }
+    pthread_mutex_lock(&pl->mu);
+    pl->st.paths += st.paths; pl->st.segments += st.segments; pl->st.sphere_tests += st.sphere_tests;
+    pl->st.rng_draws += st.rng_draws; pl->st.max_depth_hits += st.max_depth_hits;
+    pthread_mutex_unlock(&pl->mu);
+    return NULL;
+}
+EXPORT int oracle_render_sampled_rows(const oracle_scene *sc, const oracle_camera *cam, const oracle_params *p,
+                                      int row_step, int row_offset, int threads,
+                                      uint8_t *rgba, size_t stride, double *hdr, oracle_stats *stats) {
+    if (!sc || !cam || !p || row_step <= 0 || threads <= 0) return -1;
+    job_t job = {sc, cam, p, rgba, stride, hdr};
+    spool_t pl;
+    pl.job = &job; pl.step = row_step; pl.next = row_offset; pl.height = p->height;
+    memset(&pl.st, 0, sizeof pl.st);
+    pthread_mutex_init(&pl.mu, NULL);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, sample_worker, &pl);
+    for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+    free(th);
+    pthread_mutex_destroy(&pl.mu);
+    if (stats) *stats = pl.st;
+    return 0;
+}
+
 /* Tracer.RenderLines(idx, yStart, yEnd, scene) (ray/tracer.go:120): rows outside stay untouched. */
 EXPORT int oracle_render_lines(const oracle_scene *sc, const oracle_camera *cam, const oracle_params *p,
                                int idx, int y0, int y1, uint8_t *rgba, size_t stride, double *hdr, oracle_stats *stats) {

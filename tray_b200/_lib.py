@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libtraycuda.so")
+_SO = os.environ.get("TRAY_LIB") or os.path.join(_HERE, "libtraycuda.so")  # TRAY_LIB: tuning variants only
 
 # error codes / enums (include/tray_cuda.h)
 OK, E_INVALID, E_CUDA, E_NO_SCENE, E_UNSUPPORTED, E_NO_DEVICE = 0, -1, -2, -3, -4, -5

@@ -92,7 +92,9 @@ struct Device {
     int dev = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_trace_end = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_pool;  // (start, stop) pairs around every trace launch of the last render
+    int ev_used = 0;
     // scene
     int n = 0, n_pad = 0;
     double4* geo_d = nullptr; float4* geo_f = nullptr;
@@ -111,6 +113,15 @@ struct Device {
     int passes = 0;
 };
 
+cudaEvent_t next_event(Device& d) {
+    if (d.ev_used == (int)d.ev_pool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        d.ev_pool.push_back(e);
+    }
+    return d.ev_pool[d.ev_used++];
+}
+
 template <typename P>
 void grow(P*& ptr, size_t& cap, size_t need) {
     if (need <= cap) return;
@@ -127,6 +138,8 @@ struct tray_ctx {
     std::string err;
     std::mutex mu;
     bool have_scene = false;
+    std::vector<double4> host_geo_d;  // host copy of the padded table (kernel-parameter path)
+    std::vector<float4> host_geo_f;
     double bg_a[3] = {1, 1, 1}, bg_b[3] = {0.4, 0.65, 1.0};
     // last render
     int width = 0, height = 0, y0 = 0, y1 = 0;
@@ -176,39 +189,53 @@ DevCamera dev_camera(const tray_camera* c) {
     return d;
 }
 
-constexpr int kTPB = 128;
-constexpr int kMinBlocks = 4;
+#ifndef TRAY_TPB
+#define TRAY_TPB 128
+#endif
+#ifndef TRAY_MINB
+#define TRAY_MINB 5
+#endif
+constexpr int kTPB = TRAY_TPB;        // threads per CTA of the trace kernel
+constexpr int kMinBlocks = TRAY_MINB; // resident CTAs per SM the register allocation targets
 constexpr size_t kSmemBudget = 200 * 1024;
+
+template <typename T, bool FMA, int GEO>
+void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S, const GeoArg<T, GEO>& GP, size_t smem) {
+    auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, GEO>;
+    int bps = 0;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+    if (bps < 1) bps = 1;
+    k<<<d.num_sms * bps, kTPB, smem, d.stream>>>(A, S, GP);
+    CK(cudaGetLastError());
+}
 
 template <typename T, bool FMA>
 struct TraceLaunch {
-    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S) {
+    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo) {
         typedef typename Vec4T<T>::type T4;
-        size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
-        size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
-        bool smem_geo = geo_bytes + tail <= kSmemBudget;
-        size_t smem = (smem_geo ? geo_bytes : 0) + tail;
-        int bps = 0;
-        if (smem_geo) {
-            auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, true>;
-            CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
-            if (bps < 1) bps = 1;
-            k<<<d.num_sms * bps, kTPB, smem, d.stream>>>(A, S);
+        const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
+        const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
+        if (TRAY_PARAM_GEO && S.n_pad <= kParamSpheres) {
+            // small scene: the table travels in the kernel parameters (constant bank, uniform loads)
+            static thread_local GeoArg<T, kGeoParam> gp;
+            memcpy(gp.g, host_geo, geo_bytes);
+            for (int i = S.n_pad; i < kParamSpheres; i++) gp.g[i] = ((const T4*)host_geo)[S.n_pad - 1];
+            launch_trace_geo<T, FMA, kGeoParam>(d, A, S, gp, tail);
+        } else if (geo_bytes + tail <= kSmemBudget) {
+            GeoArg<T, kGeoShared> none{};
+            launch_trace_geo<T, FMA, kGeoShared>(d, A, S, none, geo_bytes + tail);
         } else {
-            auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, false>;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
-            if (bps < 1) bps = 1;
-            k<<<d.num_sms * bps, kTPB, smem, d.stream>>>(A, S);
+            GeoArg<T, kGeoGlobal> none{};
+            launch_trace_geo<T, FMA, kGeoGlobal>(d, A, S, none, tail);
         }
-        CK(cudaGetLastError());
     }
 };
 
 void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision) {
-    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d));
-    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d));
-    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d));
+    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
 }
 
 constexpr int kBandRows = 8;
@@ -248,7 +275,7 @@ int tray_init(const int* devices, int n_devices, tray_ctx** out) {
             d.num_sms = prop.multiProcessorCount;
             CK(cudaSetDevice(id));
             CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-            CK(cudaEventCreate(&d.ev_begin)); CK(cudaEventCreate(&d.ev_trace_end)); CK(cudaEventCreate(&d.ev_end));
+            CK(cudaEventCreate(&d.ev_begin)); CK(cudaEventCreate(&d.ev_end));
             CK(cudaMalloc(&d.stats, 8 * sizeof(unsigned long long)));
             CK(cudaMemset(d.stats, 0, 8 * sizeof(unsigned long long)));
             CK(cudaMalloc(&d.srgb_thr, 256 * sizeof(double)));
@@ -290,7 +317,7 @@ void tray_destroy(tray_ctx* ctx) {
         cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stats); cudaFree(d.srgb_thr);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
-        if (d.ev_trace_end) cudaEventDestroy(d.ev_trace_end);
+        for (cudaEvent_t e : d.ev_pool) cudaEventDestroy(e);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -308,7 +335,7 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
     for (int i = 0; i < sc->n; i++)
         if (sc->mat_kind[i] > TRAY_MAT_DIELECTRIC) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_scene_upload: unknown material kind (only Lambertian/Metal/Dielectric spheres are supported; no CPU fallback)");
     try {
-        int n = sc->n, n_pad = std::max(4, (n + 3) / 4 * 4);
+        int n = sc->n, n_pad = std::max(8, (n + 7) / 8 * 8);  // the hot loop consumes chunks of 8
         const double ninf = -std::numeric_limits<double>::infinity();
         std::vector<double4> gd(n_pad); std::vector<float4> gf(n_pad);
         std::vector<double> rd(n_pad, 1.0); std::vector<float> rf(n_pad, 1.0f);
@@ -343,6 +370,7 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
         }
         for (int i = 0; i < 3; i++) { ctx->bg_a[i] = sc->bg_a[i]; ctx->bg_b[i] = sc->bg_b[i]; }
+        ctx->host_geo_d = gd; ctx->host_geo_f = gf;
         ctx->have_scene = true;
     } catch (const std::exception& ex) {
         return fail(ctx, TRAY_E_CUDA, ex.what());
@@ -402,7 +430,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->width = p->width; ctx->height = p->height; ctx->y0 = p->y0; ctx->y1 = p->y1;
         ctx->have_image = false; ctx->have_hdr = false;
         ctx->progress_base = 0; ctx->progress_spp = p->spp; ctx->rendering = true;
-        for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; }
+        for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; d.ev_used = 0; }
         DevCamera dcam = dev_camera(cam);
         const int ext_count = p->shard_count > 1 ? p->shard_count : 1;
         const int ext_index = p->shard_count > 1 ? p->shard_index : 0;
@@ -432,6 +460,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
             CK(cudaEventRecord(d.ev_begin, d.stream));
             if (rows > 0) {
+                CK(cudaEventRecord(next_event(d), d.stream));
                 size_t smem = (size_t)d.n_pad * sizeof(double4) + sizeof(ZigTables);
                 DevScene<double> S = dev_scene<double>(ctx, d);
                 if (p->precision == TRAY_FP64_FMA) {
@@ -442,9 +471,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     reference_stream_kernel<false><<<A.n_chunks, 32, smem, d.stream>>>(A, S);
                 }
                 CK(cudaGetLastError());
+                CK(cudaEventRecord(next_event(d), d.stream));
                 launches++;
             }
-            CK(cudaEventRecord(d.ev_trace_end, d.stream));
             CK(cudaEventRecord(d.ev_end, d.stream));
             for (int r = 0; r < rows; r++) d.local_rows.push_back(p->y0 + r);
         } else {
@@ -472,7 +501,6 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                 CK(cudaEventRecord(d.ev_begin, d.stream));
                 if (n_pixels == 0 || spp_local == 0) {
                     if (split_samples && n_pixels) CK(cudaMemsetAsync(d.hdr, 0, n_pixels * 3 * sizeof(double), d.stream));
-                    CK(cudaEventRecord(d.ev_trace_end, d.stream));
                     CK(cudaEventRecord(d.ev_end, d.stream));
                     continue;
                 }
@@ -498,7 +526,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.band_rows = kBandRows; A.shard_count = shard_count; A.shard_index = shard_index;
                     A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
+                    CK(cudaEventRecord(next_event(d), d.stream));
                     launch_trace(ctx, d, A, p->precision);
+                    CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
                     R.inv_spp = 1.0 / (double)p->spp; R.partial = split_samples ? 1 : 0;
@@ -507,7 +537,6 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     CK(cudaGetLastError());
                     launches += 2;
                 }
-                CK(cudaEventRecord(d.ev_trace_end, d.stream));
                 CK(cudaEventRecord(d.ev_end, d.stream));
             }
             if (split_samples) {
@@ -542,7 +571,11 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             CK(cudaStreamSynchronize(d.stream));
             float ms = 0, ms2 = 0;
             CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
-            CK(cudaEventElapsedTime(&ms2, d.ev_begin, d.ev_trace_end));
+            for (int e = 0; e + 1 < d.ev_used; e += 2) {
+                float t = 0;
+                CK(cudaEventElapsedTime(&t, d.ev_pool[e], d.ev_pool[e + 1]));
+                ms2 += t;
+            }
             kernel_ms = std::max(kernel_ms, (double)ms);
             trace_ms = std::max(trace_ms, (double)ms2);
             unsigned long long st[3];
@@ -689,7 +722,52 @@ uint64_t tray_progress(tray_ctx* ctx) {
 int tray_measure_peak(tray_ctx* ctx, int32_t kind, double* tflops, double* ms_out) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (!tflops || kind < 0 || kind > 2) return fail(ctx, TRAY_E_INVALID, "tray_measure_peak: bad argument");
+    if (!tflops || kind < 0 || kind > 4) return fail(ctx, TRAY_E_INVALID, "tray_measure_peak: bad argument");
+    if (kind >= 3) {  // hot-loop-only probe on the uploaded scene (3: fused, 4: strict); TFLOP/s at 18 flops per test
+        if (!ctx->have_scene) return fail(ctx, TRAY_E_NO_SCENE, "tray_measure_peak: loop probe needs a scene");
+        try {
+            Device& d = ctx->devs[0];
+            CK(cudaSetDevice(d.dev));
+            double* sink;
+            CK(cudaMalloc(&sink, 8));
+            DevScene<double> S = dev_scene<double>(ctx, d);
+            size_t smem = (size_t)S.n_pad * sizeof(double4);
+            if (smem > kSmemBudget) throw std::runtime_error("tray_measure_peak: scene too large for the loop probe");
+            const int iters = 200;
+            int bps = 0;
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            float best = 1e30f;
+            int blocks = 0;
+            for (int rep = 0; rep < 3; rep++) {
+                if (kind == 3) {
+                    auto k = hotloop_probe_kernel<double, true, kTPB, kMinBlocks>;
+                    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+                    blocks = d.num_sms * std::max(1, bps);
+                    CK(cudaEventRecord(a, d.stream));
+                    k<<<blocks, kTPB, smem, d.stream>>>(S, iters, sink);
+                } else {
+                    auto k = hotloop_probe_kernel<double, false, kTPB, kMinBlocks>;
+                    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+                    blocks = d.num_sms * std::max(1, bps);
+                    CK(cudaEventRecord(a, d.stream));
+                    k<<<blocks, kTPB, smem, d.stream>>>(S, iters, sink);
+                }
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(b, d.stream));
+                CK(cudaStreamSynchronize(d.stream));
+                float ms;
+                CK(cudaEventElapsedTime(&ms, a, b));
+                if (rep > 0) best = std::min(best, ms);
+            }
+            *tflops = 18.0 * (double)S.n * iters * (double)blocks * kTPB / (best * 1e-3) / 1e12;
+            if (ms_out) *ms_out = best;
+            cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+        } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+        return TRAY_OK;
+    }
     try {
         Device& d = ctx->devs[0];
         CK(cudaSetDevice(d.dev));

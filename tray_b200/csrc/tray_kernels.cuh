@@ -47,55 +47,92 @@ __device__ __forceinline__ T t_inf();
 template <> __device__ __forceinline__ double t_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_float(0x7f800000); }
 
-// Resolve this lane's deferred candidates in index order with the reference's running-closest rule
-// (Scene.Hit, ray/objects.go:37-46): a later sphere wins only if strictly closer.
+// Where the hot loop reads the sphere table from.
+//   kGeoParam  : the kernel-parameter constant bank (<= kParamSpheres spheres). The loop index is warp-uniform,
+//                so the loads go through the uniform datapath (ULDC) into uniform registers and the FP64
+//                instructions take them as operands: no LDS, no vector registers for sphere data.
+//   kGeoShared : SoA table staged in shared memory, broadcast LDS.128.
+//   kGeoGlobal : read-only global loads (scenes too large for shared memory).
+enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2 };
+#ifndef TRAY_CH
+#define TRAY_CH 8
+#endif
+#ifndef TRAY_PARAM_GEO
+#define TRAY_PARAM_GEO 0
+#endif
+constexpr int kParamSpheres = 960;  // 960 * 32 B = 30 KB of the 32 KB parameter space
+
+template <typename T, int GEO> struct GeoArg { char unused; };
+template <typename T> struct GeoArg<T, kGeoParam> { typename Vec4T<T>::type g[kParamSpheres]; };
+
+// One lane's deferred candidates: sphere ids in index order, in shared memory (cand[k*TPB]).
+// Resolve them with the reference's running-closest rule (Scene.Hit, ray/objects.go:37-46): a later sphere
+// wins only if strictly closer. Sphere data comes from global memory here (rare path, L1/L2 resident).
 template <typename T, bool FMA, int TPB>
-__device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type* geo, const uint16_t* cand, int ncand,
+__device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                    T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
     for (int k = 0; k < ncand; k++) {
         int id = cand[k * TPB];
-        typename Vec4T<T>::type g = geo[id];
+        typename Vec4T<T>::type g = ggeo[id];
         T h, c, disc, root;
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
         if (sphere_root<T>(h, a, disc, T(1e-6), best_t, root)) { best_t = root; best = id; }
     }
 }
 
-template <typename T, bool FMA, int TPB>
-__device__ __noinline__ void flush_candidates(const typename Vec4T<T>::type* geo, const uint16_t* cand, int ncand,
-                                              T ox, T oy, T oz, T dx, T dy, T dz, T a, T* best_t, int* best) {
-    T bt = *best_t; int b = *best;
-    resolve_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, bt, b);
-    *best_t = bt; *best = b;
+// Rare path: turn a chunk's candidate bit mask into list entries (bit 7-u <-> sphere base+u), flushing the
+// list through the full test when it is about to overflow.
+template <typename T, bool FMA, int TPB, int CH>
+__device__ __noinline__ void push_candidates(const typename Vec4T<T>::type* __restrict__ ggeo, uint16_t* cand, int* ncand_io,
+                                             unsigned mask, int base, T ox, T oy, T oz, T dx, T dy, T dz, T a,
+                                             T* best_t, int* best) {
+    int ncand = *ncand_io;
+    if (ncand > kCand - CH) {
+        T bt = *best_t; int b = *best;
+        resolve_candidates<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, bt, b);
+        *best_t = bt; *best = b;
+        ncand = 0;
+    }
+    while (mask) {
+        int bit = 31 - __clz(mask);
+        cand[ncand * TPB] = (uint16_t)(base + (CH - 1 - bit));
+        ncand++;
+        mask &= ~(1u << bit);
+    }
+    *ncand_io = ncand;
 }
 
-template <typename T, bool FMA, int TPB, int MINB, bool SMEM_GEO>
-__global__ void __launch_bounds__(TPB, MINB) trace_kernel(const TraceArgs A, const DevScene<T> S) {
+template <typename T, bool FMA, int TPB, int MINB, int GEO>
+__global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
+                                                          const __grid_constant__ GeoArg<T, GEO> GP) {
     typedef typename Vec4T<T>::type T4;
+    constexpr int CH = TRAY_CH;  // spheres per candidate-mask chunk (n_pad is a multiple of 8)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T4* sgeo = reinterpret_cast<T4*>(smem_raw);
-    const size_t geo_bytes = SMEM_GEO ? (size_t)S.n_pad * sizeof(T4) : 0;
+    const size_t geo_bytes = GEO == kGeoShared ? (size_t)S.n_pad * sizeof(T4) : 0;
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
     const int tid = threadIdx.x;
-    if (SMEM_GEO)
+    if (GEO == kGeoShared)
         for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
     zig_load(zig, tid, TPB);
     __syncthreads();
-    const T4* geo = SMEM_GEO ? sgeo : S.geo;
+    const T4* __restrict__ ggeo = S.geo;
     uint16_t* cand = cand_all + tid;  // this lane's list: cand[k*TPB]
 
     const int lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     bool has = false, exhausted = false;
-    unsigned long long pool_next = 0, pool_end = 0, my_li = 0;
+    unsigned pool_next = 0, pool_end = 0, my_li = 0;  // local sample indices of this pass (< 2^32 by construction)
+    const unsigned n_samples = (unsigned)A.n_samples;
     // Idle lanes carry a ray that certainly misses everything (every sphere is far behind it), so the
     // hot loop needs no "has a path" test.
     V3<T> O = mk<T>(T(0), T(1e18), T(0)), D = mk<T>(T(0), T(1), T(0));
     Pcg rng = pcg_new_idx(0, 0);
     int depth_left = 0, sp = 0;
     uint16_t stk[kMaxDepth];
-    unsigned long long nseg = 0, nexh = 0, ndone = 0;
+    unsigned long long nseg = 0;
+    unsigned nexh = 0, ndone = 0;
     const int n_pad = S.n_pad;
 
     for (;;) {
@@ -108,19 +145,19 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const TraceArgs A, con
                     if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)kBatch);
                     base = __shfl_sync(kFull, base, 0);
                     if (base >= A.n_samples) { exhausted = true; break; }
-                    pool_next = base;
-                    pool_end = base + kBatch < A.n_samples ? base + kBatch : A.n_samples;
+                    pool_next = (unsigned)base;
+                    pool_end = (unsigned)base + kBatch < n_samples ? (unsigned)base + kBatch : n_samples;
                 }
-                unsigned avail = (unsigned)(pool_end - pool_next);
+                unsigned avail = pool_end - pool_next;
                 unsigned rank = __popc(need & lt_mask);
                 if (!has && rank < avail) {
                     my_li = pool_next + rank;
                     // local sample -> pixel, sample number, global stream index
-                    unsigned long long lp = A.pass_pixel0 + my_li / (unsigned)A.spp_local;
+                    unsigned lp = (unsigned)A.pass_pixel0 + my_li / (unsigned)A.spp_local;
                     int j = (int)(my_li % (unsigned)A.spp_local);
                     int s = A.sample_offset + j * A.sample_stride;
                     int ly = (int)(lp / (unsigned)A.width);
-                    int x = (int)(lp - (unsigned long long)ly * (unsigned)A.width);
+                    int x = (int)(lp - (unsigned)ly * (unsigned)A.width);
                     int y = map_row(A, ly);
                     unsigned long long idx = ((unsigned long long)y * (unsigned)A.width + (unsigned)x) * (unsigned)A.spp + (unsigned)s;
                     rng = pcg_new_idx(idx, A.seed);
@@ -146,52 +183,77 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const TraceArgs A, con
         const T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
         T best_t = t_inf<T>();
         int best = -1, ncand = 0;
+        // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
+        // shift. The mask of chunk k is examined while chunk k+1 is in flight, so no branch waits on FP64 results.
+        unsigned mask_prev = 0;
 #pragma unroll 1
-        for (int i = 0; i < n_pad; i += 4) {
-            // four independent tests (ILP for the FP64 pipe), one branch per group
-            int m[4];
+        for (int i = 0; i < n_pad; i += CH) {
+            unsigned mask = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                T4 g = geo[i + u];
+            for (int u = 0; u < CH; u++) {
+                T4 g;
+                if constexpr (GEO == kGeoParam) g = GP.g[i + u];
+                else if constexpr (GEO == kGeoShared) g = sgeo[i + u];
+                else g = ggeo[i + u];
                 T h, c, disc;
                 sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
-                m[u] = miss_bits(h, c, disc);
+                mask = __funnelshift_l((unsigned)miss_bits(h, c, disc), mask, 1);  // shifts in the "missed" sign bit
             }
-            if ((m[0] & m[1] & m[2] & m[3]) >= 0) {  // some sphere of the group may be hit (rare)
-                if (ncand > kCand - 4) {
-                    flush_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
-                    ncand = 0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (m[u] >= 0) { cand[ncand * TPB] = (uint16_t)(i + u); ncand++; }
-            }
+            mask = ~mask & ((1u << CH) - 1u);  // 1 = may be hit
+            if (mask_prev)
+                push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, i - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+            mask_prev = mask;
         }
-        resolve_candidates<T, FMA, TPB>(geo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+        if (mask_prev)
+            push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+        resolve_candidates<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
 
         // ---------------- RayColor step (ray/objects.go:49-62) ----------------
         if (has) {
             nseg++;
             bool finish = false;
             V3<T> col = mk<T>(T(0), T(0), T(0));
+            // Unit(r.Direction) is needed by the sky (objects.go:69), Metal (materials.go:29) and Dielectric
+            // (materials.go:52): computed once for every lane instead of inside three divergent branches.
+            const V3<T> ud = unit(D);
             if (best < 0) {
-                col = background<T>(S.bg_a, S.bg_b, D);
+                T ab = T(0.5) * (ud.y + T(1));  // AmbientLight.Hit, objects.go:68-73
+                col = mk<T>(T(S.bg_a[0]), T(S.bg_a[1]), T(S.bg_a[2])) * (T(1) - ab) + mk<T>(T(S.bg_b[0]), T(S.bg_b[1]), T(S.bg_b[2])) * ab;
                 finish = true;
             } else {
-                T4 g = geo[best];
+                T4 g = ggeo[best];
                 V3<T> P, N;
                 bool front;
                 hit_record<T>(O, D, best_t, mk<T>(g.x, g.y, g.z), S.radius[best], P, N, front);
-                int kind = S.kind[best];
-                double4 prm = S.params[best];
-                V3<T> O2, D2;
-                bool alb;
-                bool scattered = scatter<T>(kind, prm, rng, zig, D, P, N, front, O2, D2, alb);
+                const int kind = S.kind[best];
+                const double4 prm = S.params[best];
+                // one shared UnitVector draw site for Lambertian (always) and Metal (iff Fuzz > 0)
+                const bool need_uv = kind == 0 || (kind == 1 && prm.w > 0.0);
+                V3<T> uv = mk<T>(T(0), T(0), T(0));
+                if (need_uv) { V3<double> u64 = pcg_unit_vector(rng, zig); uv = mk<T>(T(u64.x), T(u64.y), T(u64.z)); }
+                bool scattered = true;
+                V3<T> D2;
+                if (kind == 0) {  // Lambertian.Scatter, materials.go:13-21
+                    D2 = N + uv;
+                    if (near_zero(D2)) D2 = N;
+                } else if (kind == 1) {  // Metal.Scatter, materials.go:28-38
+                    D2 = reflect(ud, N);
+                    if (prm.w > 0.0) D2 = D2 + uv * T(prm.w);
+                    scattered = dot(D2, N) > T(0);
+                } else {  // Dielectric.Scatter, materials.go:44-64
+                    T ri = T(prm.x);
+                    T ratio = front ? T(1) / ri : ri;
+                    T cosTheta = tmin2(dot(vneg(ud), N), T(1));
+                    T sinTheta = tsqrt(T(1) - cosTheta * cosTheta);
+                    bool refl = ratio * sinTheta > T(1);
+                    if (!refl) refl = (double)reflectance(cosTheta, ratio) > pcg_f64(rng);  // drawn only when it can refract
+                    D2 = refl ? reflect(ud, N) : refract(ud, N, ratio);
+                }
                 if (!scattered) {
                     finish = true;  // absorbed: black
                 } else {
-                    if (alb) stk[sp++] = (uint16_t)best;
-                    O = O2; D = D2;
+                    if (kind != 2) stk[sp++] = (uint16_t)best;  // attenuation = albedo; Dielectric's (1,1,1) is an exact identity
+                    O = P; D = D2;
                     depth_left--;
                     if (depth_left <= 0) { finish = true; nexh++; }  // RayColor(depth<=0) = black
                 }
@@ -220,8 +282,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const TraceArgs A, con
     }
     if (lane == 0) {
         atomicAdd(&A.stats[0], nseg);
-        atomicAdd(&A.stats[1], nexh);
-        if (A.progress) atomicAdd(A.progress, ndone);
+        atomicAdd(&A.stats[1], (unsigned long long)nexh);
+        if (A.progress) atomicAdd(A.progress, (unsigned long long)ndone);
     }
 }
 
@@ -448,6 +510,43 @@ __global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long 
 __global__ void srgb_kernel(const double* x, int n, const double* thr, unsigned char* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = linear_to_srgb(thr, x[i]);
+}
+
+// Hot-loop-only probe: the sphere-test loop of trace_kernel with nothing around it (no shading, no regeneration,
+// rays that certainly miss), to measure the ceiling the loop itself can reach at a given occupancy.
+template <typename T, bool FMA, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) hotloop_probe_kernel(const DevScene<T> S, int iters, double* sink) {
+    typedef typename Vec4T<T>::type T4;
+    constexpr int CH = TRAY_CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T4* sgeo = reinterpret_cast<T4*>(smem_raw);
+    for (int i = threadIdx.x; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
+    __syncthreads();
+    const int gid = blockIdx.x * TPB + threadIdx.x;
+    // upward rays from high above the scene: h < 0 and c > 0 for every sphere
+    T ox = T(0.001) * T(gid & 1023), oy = T(5000), oz = T(0.002) * T(gid >> 10), dx = T(0.01), dy = T(1), dz = T(0.02);
+    const T a = dx * dx + dy * dy + dz * dz;
+    unsigned acc = 0;
+    for (int it = 0; it < iters; it++) {
+        unsigned mask_prev = 0;
+#pragma unroll 1
+        for (int i = 0; i < S.n_pad; i += CH) {
+            unsigned mask = 0;
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                T4 g = sgeo[i + u];
+                T h, c, disc;
+                sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+                mask = __funnelshift_l((unsigned)miss_bits(h, c, disc), mask, 1);
+            }
+            mask = ~mask & ((1u << CH) - 1u);
+            if (mask_prev) acc += mask_prev;
+            mask_prev = mask;
+        }
+        acc += mask_prev;
+        ox += T(1e-9);  // keep the compiler from hoisting the loop
+    }
+    if (acc == 0xdeadbeefu) sink[0] = (double)acc;
 }
 
 // Issue-bound pipe peaks (roofline denominators): 8 independent chains per thread.

@@ -264,7 +264,7 @@ class Context:
         _lib.check(self.handle, self._L.tray_read_hdr(self.handle, hdr.ctypes.data_as(C.c_void_p)))
         return hdr
 
-    def first_hit(self, cam_c, width, height, precision=FP64_FMA):
+    def first_hit(self, cam_c, width, height, precision=FP64_STRICT):
         ids = np.zeros((height, width), dtype=np.int32)
         t = np.zeros((height, width))
         nrm = np.zeros((height, width, 3))
@@ -327,7 +327,7 @@ class Tracer(Camera):
         self.imageData = np.zeros((self.height, self.width, 4), dtype=np.uint8)  # image.NewRGBA: zeroed
         # backend
         self.StreamMode = STREAM_PER_SAMPLE
-        self.Precision = FP64_FMA
+        self.Precision = FP64_STRICT  # exact Go/amd64 float64 semantics; FP64_FMA is the opt-in fused mode
         self.SplitMode = SPLIT_TILES
         self.ShardIndex, self.ShardCount = 0, 0
         self.Context = None
@@ -428,3 +428,14 @@ class Tracer(Camera):
 def New(width, height):
     """ray.New (ray/tracer.go:38-45)."""
     return Tracer(width, height)
+
+
+BAND_ROWS = 8  # kBandRows in csrc/tray_api.cu
+
+
+def shard_rows(y0, y1, shard_index, shard_count, band_rows=BAND_ROWS):
+    """Rows of [y0,y1) that shard `shard_index` of `shard_count` renders in tile mode: 8-row bands, round-robin
+    (same rule as tray_render; the reference's analogue is the row-chunk work queue, ray/tracer.go:93-103)."""
+    if shard_count <= 1:
+        return list(range(y0, y1))
+    return [y0 + r for r in range(y1 - y0) if (r // band_rows) % shard_count == shard_index]
