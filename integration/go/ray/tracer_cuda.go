@@ -1,0 +1,249 @@
+//go:build cuda
+
+// tracer_cuda.go -- cgo shim that routes (*Tracer).Render / RenderLines to libtraycuda.so (B200, sm_100a).
+//
+// Drop this file into the reference's ray/ package and build with `-tags cuda` (CGO_ENABLED=1). The pure-Go
+// bodies of Render/RenderLines in ray/tracer.go move behind `//go:build !cuda` (see INTEGRATION.md for the
+// 12-line diff). Everything else in the package -- New, the Tracer fields, Camera.Initialize, Scene, Sphere,
+// the materials, RichScene -- is unchanged, so tray and benchmark keep their flags and behaviour.
+//
+// NOT COMPILED IN THE BUILD CONTAINER (no Go toolchain there): it is kept deliberately thin -- marshalling
+// only -- and the identical C ABI is exercised from Python (ctypes) and C++ (tray_b200/host) by the test-suite.
+package ray
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../../tray_b200 -ltraycuda -Wl,-rpath,${SRCDIR}/../../../tray_b200
+#include <stdlib.h>
+#include "tray_cuda.h"
+*/
+import "C"
+
+import (
+	"crypto/rand"
+	"encoding/binary"
+	"fmt"
+	"image"
+	"os"
+	"runtime"
+	"strconv"
+	"sync"
+	"time"
+	"unsafe"
+)
+
+// Backend knobs (additive; zero values keep the drop-in defaults).
+var (
+	// CUDADevices lists the CUDA ordinals one Tracer context uses (nil = device 0). TRAY_GPUS=N sets 0..N-1.
+	CUDADevices []int
+	// CUDAReferenceStreams reproduces the reference's sequential per-chunk RNG streams (one warp per chunk,
+	// honours NumWorkers; slow by construction). Default: per-sample streams, independent of NumWorkers.
+	CUDAReferenceStreams = os.Getenv("TRAY_STREAMS") == "reference"
+	// CUDAFusedFP64 selects the fused-multiply-add discriminant (faster, not bit-identical to Go/amd64).
+	CUDAFusedFP64 = os.Getenv("TRAY_FP64") == "fma"
+	// CUDASampleSplit splits samples instead of tiles across devices (partial sums reduced over NVLink).
+	CUDASampleSplit = os.Getenv("TRAY_SPLIT") == "samples"
+)
+
+type cudaState struct {
+	mu  sync.Mutex
+	ctx *C.tray_ctx
+}
+
+var cuda cudaState
+
+func cudaContext() *C.tray_ctx {
+	if cuda.ctx != nil {
+		return cuda.ctx
+	}
+	devs := CUDADevices
+	if n, err := strconv.Atoi(os.Getenv("TRAY_GPUS")); err == nil && n > 0 && devs == nil {
+		for i := 0; i < n; i++ {
+			devs = append(devs, i)
+		}
+	}
+	var ctx *C.tray_ctx
+	var rc C.int
+	if len(devs) == 0 {
+		rc = C.tray_init(nil, 0, &ctx)
+	} else {
+		cd := make([]C.int, len(devs))
+		for i, d := range devs {
+			cd[i] = C.int(d)
+		}
+		rc = C.tray_init(&cd[0], C.int(len(cd)), &ctx)
+	}
+	if rc != 0 {
+		panic(fmt.Sprintf("tray: CUDA backend unavailable: %s", C.GoString(C.tray_last_error(nil))))
+	}
+	cuda.ctx = ctx
+	return ctx
+}
+
+// flatScene is the SoA marshalling of Scene.Objects: flat numeric slices only (cgo pointer rules).
+type flatScene struct {
+	cx, cy, cz, r []float64
+	kind          []uint8
+	params        []float64
+}
+
+func (f *flatScene) walk(objs []Hittable) error {
+	for _, o := range objs {
+		switch s := o.(type) {
+		case *Scene: // Scene satisfies Hittable (objects.go:28-46): flattened in place, order preserved
+			if err := f.walk(s.Objects); err != nil {
+				return err
+			}
+		case *Sphere:
+			var k uint8
+			var p [4]float64
+			switch m := s.Mat.(type) {
+			case Lambertian:
+				k, p = C.TRAY_MAT_LAMBERTIAN, [4]float64{m.Albedo.x, m.Albedo.y, m.Albedo.z, 0}
+			case Metal:
+				k, p = C.TRAY_MAT_METAL, [4]float64{m.Albedo.x, m.Albedo.y, m.Albedo.z, m.Fuzz}
+			case Dielectric:
+				k, p = C.TRAY_MAT_DIELECTRIC, [4]float64{m.RefIdx, 0, 0, 0}
+			default:
+				return fmt.Errorf("tray cuda: unsupported Material %T (no CPU fallback)", s.Mat)
+			}
+			f.cx = append(f.cx, s.Center.x)
+			f.cy = append(f.cy, s.Center.y)
+			f.cz = append(f.cz, s.Center.z)
+			f.r = append(f.r, s.Radius)
+			f.kind = append(f.kind, k)
+			f.params = append(f.params, p[:]...)
+		default:
+			return fmt.Errorf("tray cuda: unsupported Hittable %T (no CPU fallback)", o)
+		}
+	}
+	return nil
+}
+
+func v3(dst *[3]C.double, v Vec3) { dst[0], dst[1], dst[2] = C.double(v.x), C.double(v.y), C.double(v.z) }
+
+func ptrF(s []float64) *C.double {
+	if len(s) == 0 {
+		return nil
+	}
+	return (*C.double)(unsafe.Pointer(&s[0]))
+}
+
+func randomSeed() uint64 {
+	var b [8]byte
+	_, _ = rand.Read(b[:])
+	return binary.LittleEndian.Uint64(b[:]) | 1
+}
+
+// renderCUDA renders rows [y0,y1) into t.imageData. idx < 0: Render (chunking from NumWorkers); else RenderLines(idx).
+func (t *Tracer) renderCUDA(scene *Scene, y0, y1, idx int) error {
+	cuda.mu.Lock()
+	defer cuda.mu.Unlock()
+	ctx := cudaContext()
+	var f flatScene
+	if err := f.walk(scene.Objects); err != nil {
+		return err
+	}
+	var sd C.tray_scene_desc
+	sd.n = C.int32_t(len(f.cx))
+	sd.cx, sd.cy, sd.cz, sd.radius, sd.mat_params = ptrF(f.cx), ptrF(f.cy), ptrF(f.cz), ptrF(f.r), ptrF(f.params)
+	if len(f.kind) > 0 {
+		sd.mat_kind = (*C.uint8_t)(unsafe.Pointer(&f.kind[0]))
+	}
+	v3(&sd.bg_a, scene.Background.ColorA)
+	v3(&sd.bg_b, scene.Background.ColorB)
+	if rc := C.tray_scene_upload(ctx, &sd); rc != 0 {
+		return fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+	}
+	var cam C.tray_camera
+	v3(&cam.position, t.Position)
+	v3(&cam.pixel00, t.pixel00)
+	v3(&cam.pixel_x, t.pixelXVector)
+	v3(&cam.pixel_y, t.pixelYVector)
+	v3(&cam.defocus_u, t.defocusDiskU)
+	v3(&cam.defocus_v, t.defocusDiskV)
+	cam.aperture, cam.focus_distance, cam.focal_length = C.double(t.Aperture), C.double(t.FocusDistance), C.double(t.FocalLength)
+	var p C.tray_params
+	p.width, p.height = C.int32_t(t.width), C.int32_t(t.height)
+	p.spp, p.max_depth, p.ray_radius = C.int32_t(t.NumRaysPerPixel), C.int32_t(t.MaxDepth), C.double(t.RayRadius)
+	seed := t.Seed
+	if seed == 0 { // "0 means randomized each time" (tracer.go:32)
+		seed = randomSeed()
+	}
+	p.seed = C.uint64_t(seed)
+	p.y0, p.y1 = C.int32_t(y0), C.int32_t(y1)
+	p.stream_mode = C.TRAY_STREAM_PER_SAMPLE
+	if CUDAReferenceStreams {
+		p.stream_mode = C.TRAY_STREAM_REFERENCE
+	}
+	p.num_workers, p.stream_idx = C.int32_t(t.NumWorkers), -1
+	if idx >= 0 {
+		p.num_workers, p.stream_idx = 0, C.int64_t(idx)
+	}
+	p.precision = C.TRAY_FP64_STRICT
+	if CUDAFusedFP64 {
+		p.precision = C.TRAY_FP64_FMA
+	}
+	if CUDASampleSplit {
+		p.split_mode = C.TRAY_SPLIT_SAMPLES
+	}
+	// ProgressFunc: poll the library from a goroutine; deltas sum to the pixel count (tracer_test.go:172-186).
+	done := make(chan struct{})
+	var wg sync.WaitGroup
+	total, sent := (y1-y0)*t.width, 0
+	if t.ProgressFunc != nil {
+		wg.Add(1)
+		go func() {
+			defer wg.Done()
+			tick := time.NewTicker(20 * time.Millisecond)
+			defer tick.Stop()
+			for {
+				select {
+				case <-done:
+					return
+				case <-tick.C:
+					if cur := min(int(C.tray_progress(ctx)), total); cur > sent {
+						t.ProgressFunc(cur - sent)
+						sent = cur
+					}
+				}
+			}
+		}()
+	}
+	pix := t.imageData.Pix
+	var st C.tray_stats
+	rc := C.tray_render(ctx, &cam, &p, (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.size_t(t.imageData.Stride), &st)
+	close(done)
+	wg.Wait()
+	runtime.KeepAlive(f)
+	if rc != 0 {
+		return fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+	}
+	if t.ProgressFunc != nil && total > sent {
+		t.ProgressFunc(total - sent)
+	}
+	return nil
+}
+
+// Render performs the ray tracing and returns the resulting image data (same contract as the pure-Go Render).
+func (t *Tracer) Render(scene *Scene) *image.RGBA {
+	scene = t.prepare(scene) // the defaulting block of tracer.go:49-83, unchanged, factored into a helper
+	if err := t.renderCUDA(scene, 0, t.height, -1); err != nil {
+		panic(err) // Render has no error return; RenderErr is the additive variant
+	}
+	return t.imageData
+}
+
+// RenderErr is Render with an error return (additive API).
+func (t *Tracer) RenderErr(scene *Scene) (*image.RGBA, error) {
+	scene = t.prepare(scene)
+	err := t.renderCUDA(scene, 0, t.height, -1)
+	return t.imageData, err
+}
+
+// RenderLines renders rows [yStart,yEnd) only; idx is the stream index in reference-stream mode.
+func (t *Tracer) RenderLines(idx, yStart, yEnd int, scene *Scene) {
+	if err := t.renderCUDA(scene, yStart, yEnd, idx); err != nil {
+		panic(err)
+	}
+}
