@@ -57,8 +57,11 @@ extern "C" {
 
 /* arithmetic modes */
 #define TRAY_FP64_FMA 0    /* float64; Sphere.Hit discriminant uses fused multiply-add (11 FP64 ops/test) */
-#define TRAY_FP64_STRICT 1 /* float64; every op rounded separately = Go/amd64 semantics (17 FP64 ops/test) */
+#define TRAY_FP64_STRICT 1 /* float64; every op rounded separately = Go/amd64 semantics. DEFAULT. The sphere loop runs an
+                              fp32 conservative pre-filter (packed FFMA2) that skips a test only when it PROVES the
+                              strict fp64 test returns false; survivors get the exact 17-op fp64 test: same bits. */
 #define TRAY_FP32 2        /* float32 fast path (reported separately, PSNR vs fp64) */
+#define TRAY_FP64_STRICT_BRUTE 3 /* as STRICT but every test in fp64 (no pre-filter): the pure FP64-pipe kernel */
 
 /* multi-GPU partitioning inside one context */
 #define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */

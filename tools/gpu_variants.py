@@ -12,7 +12,7 @@ def tr(w,h,spp,d,prec):
     t = ray.New(w,h); t.Camera = ray.RichSceneCamera(); t.MaxDepth, t.NumRaysPerPixel, t.Seed, t.Precision = d, spp, 2, prec
     return t
 out = {}
-for prec, fma, name in ((ray.FP64_FMA,1,"fma"),(ray.FP64_STRICT,0,"strict")):
+for prec, fma, name in ((ray.FP64_STRICT_BRUTE,0,"fma"),(ray.FP64_STRICT,0,"strict")):
     t = tr(400,225,10,50,prec); img = t.Render(scene).copy()
     ref,_,st = O.render(O.rich_scene(2), O.camera_init(400,225,**O.RICH_CAMERA), O.make_params(400,225,spp=10,max_depth=50,seed=2,num_workers=8,stream_mode=1,fma_mode=fma))
     ok = bool(np.array_equal(img, ref))
@@ -33,7 +33,7 @@ for lib in libs:
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
     try:
         d = json.loads(line)
-        print("%-34s fma: %6.1f ms %6.1f Mp/s %5.2f TF parity=%s | strict: %6.1f ms %6.1f Mp/s %5.2f TF parity=%s" % (
+        print("%-34s brute: %6.1f ms %6.1f Mp/s %5.2f TF parity=%s | filtered: %6.1f ms %6.1f Mp/s %5.2f TF parity=%s" % (
             os.path.basename(lib), d["fma"]["ms"], d["fma"]["mpaths"], d["fma"]["tflops"], d["fma"]["parity"],
             d["strict"]["ms"], d["strict"]["mpaths"], d["strict"]["tflops"], d["strict"]["parity"]),
             "| loop-only probe TF fma %.2f strict %.2f (dfma peak %.2f)" % (d["probe"]["fma"], d["probe"]["strict"], d["probe"]["dfma"]))

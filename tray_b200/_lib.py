@@ -10,7 +10,7 @@ _SO = os.environ.get("TRAY_LIB") or os.path.join(_HERE, "libtraycuda.so")  # TRA
 OK, E_INVALID, E_CUDA, E_NO_SCENE, E_UNSUPPORTED, E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 STREAM_REFERENCE, STREAM_PER_SAMPLE = 0, 1
-FP64_FMA, FP64_STRICT, FP32 = 0, 1, 2
+FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",

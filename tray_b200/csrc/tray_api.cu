@@ -100,6 +100,7 @@ struct Device {
     double4* geo_d = nullptr; float4* geo_f = nullptr;
     double* radius_d = nullptr; float* radius_f = nullptr;
     uint8_t* kind = nullptr; double4* params = nullptr;
+    float4* fpair = nullptr; float filt_mc = 0, filt_r2max = 0;
     // work buffers (grown on demand)
     double* scratch = nullptr; size_t scratch_cap = 0;  // doubles
     uint8_t* rgba = nullptr; size_t rgba_cap = 0;       // bytes
@@ -162,6 +163,7 @@ int fail(tray_ctx* ctx, int code, const std::string& msg) {
 void free_scene(Device& d) {
     cudaSetDevice(d.dev);
     cudaFree(d.geo_d); cudaFree(d.geo_f); cudaFree(d.radius_d); cudaFree(d.radius_f); cudaFree(d.kind); cudaFree(d.params);
+    cudaFree(d.fpair); d.fpair = nullptr;
     d.geo_d = nullptr; d.geo_f = nullptr; d.radius_d = nullptr; d.radius_f = nullptr; d.kind = nullptr; d.params = nullptr;
 }
 
@@ -169,12 +171,14 @@ template <typename T> DevScene<T> dev_scene(const tray_ctx* ctx, const Device& d
 template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device& d) {
     DevScene<double> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
+    s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
 template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& d) {
     DevScene<float> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
+    s.fpair = nullptr; s.filt_mc = 0; s.filt_r2max = 0;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
@@ -201,7 +205,10 @@ constexpr size_t kSmemBudget = 200 * 1024;
 
 template <typename T, bool FMA, int GEO>
 void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S, const GeoArg<T, GEO>& GP, size_t smem) {
-    auto k = trace_kernel<T, FMA, kTPB, kMinBlocks, GEO>;
+    // register budget: the pre-filter kernel keeps both the fp32 filter state and the fp64 ray live: 128 regs x 16 warps/SM
+    // measured best (140.8 vs 143.3 ms); the pure-fp64 kernels prefer 96 regs x 20 warps/SM (211.8 vs 216.7 ms).
+    constexpr int minb = (GEO == kGeoFilter && kMinBlocks > 4) ? 4 : kMinBlocks;
+    auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
@@ -212,10 +219,17 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 
 template <typename T, bool FMA>
 struct TraceLaunch {
-    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo) {
+    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false) {
         typedef typename Vec4T<T>::type T4;
         const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
         const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
+        if constexpr (sizeof(T) == 8) {
+            if (filter && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
+                GeoArg<T, kGeoFilter> none{};
+                launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
+                return;
+            }
+        }
         if (TRAY_PARAM_GEO && S.n_pad <= kParamSpheres) {
             // small scene: the table travels in the kernel parameters (constant bank, uniform loads)
             static thread_local GeoArg<T, kGeoParam> gp;
@@ -234,7 +248,8 @@ struct TraceLaunch {
 
 void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision) {
     if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
-    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true);
+    else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
     else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
 }
 
@@ -335,7 +350,8 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
     for (int i = 0; i < sc->n; i++)
         if (sc->mat_kind[i] > TRAY_MAT_DIELECTRIC) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_scene_upload: unknown material kind (only Lambertian/Metal/Dielectric spheres are supported; no CPU fallback)");
     try {
-        int n = sc->n, n_pad = std::max(8, (n + 7) / 8 * 8);  // the hot loop consumes chunks of 8
+        const int ch = TRAY_CH > 8 ? TRAY_CH : 8;
+        int n = sc->n, n_pad = std::max(ch, (n + ch - 1) / ch * ch);  // the hot loop consumes chunks of TRAY_CH spheres
         const double ninf = -std::numeric_limits<double>::infinity();
         std::vector<double4> gd(n_pad); std::vector<float4> gf(n_pad);
         std::vector<double> rd(n_pad, 1.0); std::vector<float> rf(n_pad, 1.0f);
@@ -354,11 +370,36 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
                 pr[i] = make_double4(0, 0, 0, 0);
             }
         }
+        // fp32 pre-filter table: pairs of spheres, two float4 each. Spheres whose magnitudes would blow up the
+        // filter's error bound (|c|_inf > 256 or r*r > 256, e.g. the r=1000 ground sphere) are stored as NaN:
+        // never "certainly missed", i.e. always exact-tested. Padding: r2 = -inf (always missed).
+        std::vector<float4> fp((size_t)n_pad);
+        float mc = 0.f, r2max = 0.f;
+        const float qnan = std::numeric_limits<float>::quiet_NaN(), finf = std::numeric_limits<float>::infinity();
+        for (int j = 0; j < n_pad / 2; j++) {
+            float c[2][3], nr2[2];
+            for (int k = 0; k < 2; k++) {
+                int i = 2 * j + k;
+                if (i >= n) { c[k][0] = c[k][1] = c[k][2] = 0.f; nr2[k] = finf; continue; }  // -r2 = +inf
+                double cm = std::max(std::fabs(sc->cx[i]), std::max(std::fabs(sc->cy[i]), std::fabs(sc->cz[i])));
+                double r2 = sc->radius[i] * sc->radius[i];
+                if (!(cm <= 256.0) || !(r2 <= 256.0)) { c[k][0] = c[k][1] = c[k][2] = qnan; nr2[k] = qnan; continue; }
+                c[k][0] = (float)sc->cx[i]; c[k][1] = (float)sc->cy[i]; c[k][2] = (float)sc->cz[i];
+                nr2[k] = -(float)r2;
+                mc = std::max(mc, (float)cm * 1.0000002f);
+                r2max = std::max(r2max, (float)r2 * 1.0000002f);
+            }
+            fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+            fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nr2[0], nr2[1]);
+        }
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
             free_scene(d);
             d.n = n; d.n_pad = n_pad;
+            d.filt_mc = mc; d.filt_r2max = r2max;
+            CK(cudaMalloc(&d.fpair, sizeof(float4) * n_pad));
+            CK(cudaMemcpy(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
             CK(cudaMalloc(&d.geo_d, sizeof(double4) * n_pad)); CK(cudaMalloc(&d.geo_f, sizeof(float4) * n_pad));
             CK(cudaMalloc(&d.radius_d, sizeof(double) * n_pad)); CK(cudaMalloc(&d.radius_f, sizeof(float) * n_pad));
             CK(cudaMalloc(&d.kind, n_pad)); CK(cudaMalloc(&d.params, sizeof(double4) * n_pad));
@@ -420,7 +461,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (p->max_depth > kMaxDepth) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_render: max_depth > 256");
     if (p->y0 < 0 || p->y1 > p->height || p->y0 > p->y1) return fail(ctx, TRAY_E_INVALID, "tray_render: bad row range");
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
-    if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP32) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
+    if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP64_STRICT_BRUTE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
     const int rows = p->y1 - p->y0;
@@ -655,7 +696,7 @@ int tray_first_hit(tray_ctx* ctx, const tray_camera* cam, int32_t width, int32_t
         DevCamera dc = dev_camera(cam);
         unsigned blocks = (unsigned)((n + 127) / 128);
         if (precision == TRAY_FP64_FMA) first_hit_kernel<double, true><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
-        else if (precision == TRAY_FP64_STRICT) first_hit_kernel<double, false><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
+        else if (precision == TRAY_FP64_STRICT || precision == TRAY_FP64_STRICT_BRUTE) first_hit_kernel<double, false><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
         else first_hit_kernel<float, true><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<float>(ctx, d), width, height, d_id, d_t, d_n, d_f);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d.stream));
@@ -722,8 +763,8 @@ uint64_t tray_progress(tray_ctx* ctx) {
 int tray_measure_peak(tray_ctx* ctx, int32_t kind, double* tflops, double* ms_out) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
-    if (!tflops || kind < 0 || kind > 4) return fail(ctx, TRAY_E_INVALID, "tray_measure_peak: bad argument");
-    if (kind >= 3) {  // hot-loop-only probe on the uploaded scene (3: fused, 4: strict); TFLOP/s at 18 flops per test
+    if (!tflops || kind < 0 || kind > 5) return fail(ctx, TRAY_E_INVALID, "tray_measure_peak: bad argument");
+    if (kind == 3 || kind == 4) {  // hot-loop-only probe on the uploaded scene (3: fused, 4: strict); TFLOP/s at 18 flops per test
         if (!ctx->have_scene) return fail(ctx, TRAY_E_NO_SCENE, "tray_measure_peak: loop probe needs a scene");
         try {
             Device& d = ctx->devs[0];
@@ -781,6 +822,7 @@ int tray_measure_peak(tray_ctx* ctx, int32_t kind, double* tflops, double* ms_ou
             CK(cudaEventRecord(a, d.stream));
             if (kind == 0) peak_kernel<0><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
             else if (kind == 1) peak_kernel<1><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
+            else if (kind == 5) peak_kernel<5><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
             else peak_kernel<2><<<blocks, tpb, 0, d.stream>>>(sink, iters, 1e-9);
             CK(cudaGetLastError());
             CK(cudaEventRecord(b, d.stream));
@@ -790,7 +832,7 @@ int tray_measure_peak(tray_ctx* ctx, int32_t kind, double* tflops, double* ms_ou
             if (rep > 0) best = std::min(best, ms);
         }
         // ops: every chain step is 2 flops (fma, or mul+add)
-        double flops = 2.0 * 8 * (double)iters * (double)blocks * tpb;
+        double flops = 2.0 * 8 * (double)iters * (double)blocks * tpb * (kind == 5 ? 2.0 : 1.0);
         *tflops = flops / (best * 1e-3) / 1e12;
         if (ms_out) *ms_out = best;
         cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);

@@ -15,7 +15,10 @@
 namespace tray {
 
 constexpr int kMaxDepth = 256;   // attenuation-stack capacity (ids); tray_render rejects larger MaxDepth
-constexpr int kCand = 8;         // deferred candidates per lane before an in-loop flush
+#ifndef TRAY_CH
+#define TRAY_CH 8
+#endif
+constexpr int kCand = TRAY_CH + 8;  // deferred candidates per lane before an in-loop flush
 constexpr int kBatch = 128;      // samples a warp takes from the global counter at a time
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -53,10 +56,7 @@ template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_fl
 //                instructions take them as operands: no LDS, no vector registers for sphere data.
 //   kGeoShared : SoA table staged in shared memory, broadcast LDS.128.
 //   kGeoGlobal : read-only global loads (scenes too large for shared memory).
-enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2 };
-#ifndef TRAY_CH
-#define TRAY_CH 8
-#endif
+enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3 };
 #ifndef TRAY_PARAM_GEO
 #define TRAY_PARAM_GEO 0
 #endif
@@ -109,12 +109,15 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     constexpr int CH = TRAY_CH;  // spheres per candidate-mask chunk (n_pad is a multiple of 8)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T4* sgeo = reinterpret_cast<T4*>(smem_raw);
-    const size_t geo_bytes = GEO == kGeoShared ? (size_t)S.n_pad * sizeof(T4) : 0;
+    const size_t geo_bytes = GEO == kGeoShared ? (size_t)S.n_pad * sizeof(T4) : (GEO == kGeoFilter ? (size_t)S.n_pad * 16 : 0);
+    float4* sfp = reinterpret_cast<float4*>(smem_raw);  // kGeoFilter: n_pad/2 pairs x 2 float4
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
     const int tid = threadIdx.x;
     if (GEO == kGeoShared)
         for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
+    if (GEO == kGeoFilter)
+        for (int i = tid; i < S.n_pad; i += TPB) sfp[i] = S.fpair[i];
     zig_load(zig, tid, TPB);
     __syncthreads();
     const T4* __restrict__ ggeo = S.geo;
@@ -183,9 +186,58 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         const T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
         T best_t = t_inf<T>();
         int best = -1, ncand = 0;
+        unsigned mask_prev = 0;
+        if constexpr (GEO == kGeoFilter) {
+            // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction) ----
+            // A test is skipped only when the fp32 evaluation PROVES the strict fp64 test returns false
+            // ("exact pre-filter"): with T = K1*L + K2 bounding every fp32/conversion error,
+            //   val1 = h^2 - a*(C - T) < 0            =>  disc < 0 in exact and in fp64 arithmetic
+            //   h + sqrt(a)*T < 0  and  C - T >= 0    =>  h < 0 <= c                  (both roots <= 0)
+            // Everything else (incl. NaN entries = spheres outside the filter's range) goes to the exact path.
+            const float u32 = 5.9604645e-8f;
+            const float fox = (float)(double)ox, foy = (float)(double)oy, foz = (float)(double)oz;
+            const float fdx = (float)(double)dx, fdy = (float)(double)dy, fdz = (float)(double)dz;
+            const float fa = (float)(double)a;
+            const float mo = fmaxf(fabsf(fox), fmaxf(fabsf(foy), fabsf(foz)));
+            const float eps = 5.3f * u32 * (S.filt_mc + mo);          // >= sqrt(3)*3u*(|c|+|o|): |oc_f - oc|_2
+            float k1 = 1.01f * (64.0f * u32 + 3.0f * eps);
+            float k2 = 1.01f * (3.0f * eps + 6.0f * eps * eps + 16.0f * u32 * S.filt_r2max + 8.0f * u32 + 1e-30f);
+            if (!(eps < 0.25f)) k2 = __int_as_float(0x7f800000);      // origin too far out: filter off for this ray
+            const float2 nO_x = make_float2(-fox, -fox), nO_y = make_float2(-foy, -foy), nO_z = make_float2(-foz, -foz);
+            const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
+            const float2 nA = make_float2(-fa, -fa);
+            const float saf = 1.001f * sqrtf(fa);
+            const float2 SA = make_float2(saf, saf), K1 = make_float2(k1, k1), K2 = make_float2(k2, k2);
+            const float2 nK2 = make_float2(-k2, -k2), OMK1 = make_float2(1.0f - k1, 1.0f - k1);
+#pragma unroll 1
+            for (int i = 0; i < n_pad; i += CH) {
+                unsigned mask = 0;
+#pragma unroll
+                for (int u = 0; u < CH / 2; u++) {
+                    const float4 g0 = sfp[i + 2 * u], g1 = sfp[i + 2 * u + 1];
+                    float2 ocx = __fadd2_rn(make_float2(g0.x, g0.y), nO_x);
+                    float2 ocy = __fadd2_rn(make_float2(g0.z, g0.w), nO_y);
+                    float2 ocz = __fadd2_rn(make_float2(g1.x, g1.y), nO_z);
+                    float2 h = __ffma2_rn(Dz, ocz, __ffma2_rn(Dy, ocy, __fmul2_rn(Dx, ocx)));
+                    float2 L = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __fmul2_rn(ocx, ocx)));
+                    float2 nr2k = __fadd2_rn(make_float2(g1.z, g1.w), nK2);   // -(r2 + K2)
+                    float2 cm = __ffma2_rn(L, OMK1, nr2k);                     // C - T
+                    float2 t = __ffma2_rn(K1, L, K2);                          // T
+                    float2 v1 = __ffma2_rn(h, h, __fmul2_rn(nA, cm));          // h^2 - a*(C - T)
+                    float2 v2 = __ffma2_rn(SA, t, h);                          // h + sqrt(a)*T
+                    int mx = __float_as_int(v1.x) | (__float_as_int(v2.x) & ~__float_as_int(cm.x));
+                    int my = __float_as_int(v1.y) | (__float_as_int(v2.y) & ~__float_as_int(cm.y));
+                    mask = __funnelshift_l((unsigned)mx, mask, 1);
+                    mask = __funnelshift_l((unsigned)my, mask, 1);
+                }
+                mask = has ? (~mask & ((1u << CH) - 1u)) : 0u;  // 1 = must be tested exactly (idle lanes: nothing)
+                if (mask_prev)
+                    push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, i - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                mask_prev = mask;
+            }
+        } else {
         // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
         // shift. The mask of chunk k is examined while chunk k+1 is in flight, so no branch waits on FP64 results.
-        unsigned mask_prev = 0;
 #pragma unroll 1
         for (int i = 0; i < n_pad; i += CH) {
             unsigned mask = 0;
@@ -203,6 +255,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             if (mask_prev)
                 push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, i - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
             mask_prev = mask;
+        }
         }
         if (mask_prev)
             push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
@@ -552,7 +605,20 @@ __global__ void __launch_bounds__(TPB, MINB) hotloop_probe_kernel(const DevScene
 // Issue-bound pipe peaks (roofline denominators): 8 independent chains per thread.
 template <int KIND>
 __global__ void __launch_bounds__(256) peak_kernel(double* sink, int iters, double seedv) {
-    if (KIND == 2) {
+    if (KIND == 5) {  // packed FFMA2 (two fp32 FMAs per instruction, sm_100+)
+        float2 acc[8];
+        float2 m = make_float2(1.0000001f, 0.9999999f), b = make_float2((float)seedv, (float)seedv * 2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = make_float2((float)(threadIdx.x + k), (float)k);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = __ffma2_rn(acc[k], m, b);
+        }
+        float s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += acc[k].x + acc[k].y;
+        if (s == 12345.678f) sink[0] = s;
+    } else if (KIND == 2) {
         float acc[8];
         float m = 1.0000001f, b = (float)seedv;
 #pragma unroll
