@@ -71,12 +71,27 @@ template <typename T> struct GeoArg<T, kGeoParam> { typename Vec4T<T>::type g[kP
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                    T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
+    const T tmin = T(1e-6);
     for (int k = 0; k < ncand; k++) {
         int id = cand[k * TPB];
         typename Vec4T<T>::type g = ggeo[id];
         T h, c, disc, root;
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
-        if (sphere_root<T>(h, a, disc, T(1e-6), best_t, root)) { best_t = root; best = id; }
+        if (certainly_missed(h, c, disc)) continue;  // false positives of the fp32 pre-filter: exact, no sqrt/div
+        // Sphere.Hit, objects.go:90-97. A division whose quotient certainly falls outside (tmin, best_t) is skipped:
+        // fl(x/a) >= best_t whenever x >= best_t*a*(1+2^-50), fl(x/a) <= tmin whenever x <= tmin*a*(1-2^-50)
+        // (a > 0; one rounding in the product, one in the quotient). The accepted root is computed exactly as written.
+        T sq = tsqrt(disc);
+        const T up = sizeof(T) == 8 ? T(1.0000000000000009) : T(1.000001), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
+        const T hi = best_t * a * up, lo = tmin * a * dn;
+        T x = h - sq;
+        bool ok = false;
+        if (x < hi && x > lo) { root = x / a; ok = root > tmin && root < best_t; }
+        if (!ok) {
+            x = h + sq;
+            if (x < hi && x > lo) { root = x / a; ok = root > tmin && root < best_t; }
+        }
+        if (ok) { best_t = root; best = id; }
     }
 }
 
@@ -231,8 +246,18 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                     mask = __funnelshift_l((unsigned)my, mask, 1);
                 }
                 mask = has ? (~mask & ((1u << CH) - 1u)) : 0u;  // 1 = must be tested exactly (idle lanes: nothing)
-                if (mask_prev)
-                    push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, i - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                if (mask_prev) {
+                    if (ncand > kCand - CH) {  // list about to overflow (rare): run the exact test on what is queued
+                        push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                    }
+                    unsigned m = mask_prev;
+                    do {  // append in index order: bit CH-1-u <-> sphere (i-CH)+u
+                        int bit = 31 - __clz(m);
+                        cand[ncand * TPB] = (uint16_t)(i - 1 - bit);
+                        ncand++;
+                        m &= ~(1u << bit);
+                    } while (m);
+                }
                 mask_prev = mask;
             }
         } else {
