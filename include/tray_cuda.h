@@ -63,6 +63,11 @@ extern "C" {
 #define TRAY_FP32 2        /* float32 fast path (reported separately, PSNR vs fp64) */
 #define TRAY_FP64_STRICT_BRUTE 3 /* as STRICT but every test in fp64 (no pre-filter): the pure FP64-pipe kernel */
 
+/* closest-hit structure. Results are identical for all of them (ties resolve to the lowest index). */
+#define TRAY_ACCEL_AUTO 0  /* brute force up to 2048 spheres, BVH above */
+#define TRAY_ACCEL_BRUTE 1 /* linear scan of the sphere table (the reference's Scene.Hit order) */
+#define TRAY_ACCEL_BVH 2   /* small BVH (median split, <= 4 spheres per leaf) built on the host at upload */
+
 /* multi-GPU partitioning inside one context */
 #define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */
 #define TRAY_SPLIT_SAMPLES 1 /* each GPU renders samples s == g (mod G); partial sums reduced over NVLink */
@@ -103,7 +108,8 @@ typedef struct {
     int32_t shard_index, shard_count; /* multi-process tile sharding: this context renders only the
                              row bands b with b % shard_count == shard_index (0,1 or 0,0 = everything);
                              rows of other shards in the output are left untouched */
-    int32_t reserved[5];
+    int32_t accel;        /* TRAY_ACCEL_*: closest-hit structure (0 = automatic) */
+    int32_t reserved[4];
 } tray_params;
 
 typedef struct {

@@ -266,15 +266,57 @@ def test_reference_stream_render_lines(ctx, O):
     assert np.array_equal(t.imageData, ref)
 
 
-# ---- large scene (global-memory sphere table), BASELINE config 4 shape at a small image ------------------
+# ---- closest-hit structures: BVH == filtered linear scan == pure fp64 linear scan == oracle ---------------------
+def test_bvh_and_brute_force_agree_bit_for_bit(ctx, O):
+    w, h, spp, depth = 160, 90, 6, 50
+    scene = ray.RichScene(rand.New(2))
+    ref, hdr, st = O.render(O.rich_scene(2), O.camera_init(w, h, **O.RICH_CAMERA),
+                            O.make_params(w, h, spp=spp, max_depth=depth, seed=2, num_workers=8, stream_mode=1), want_hdr=True)
+    tests = {}
+    for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH):
+        for precision in (ray.FP64_STRICT, ray.FP64_STRICT_BRUTE):
+            t = tracer(w, h, spp, depth, precision=precision)
+            t.Accel = accel
+            img = t.Render(scene)
+            assert np.array_equal(img, ref) and np.array_equal(ctx.read_hdr(w, h), hdr), (accel, precision)
+            assert t.Stats["segments"] == st["segments"]
+            tests[accel] = t.Stats["sphere_tests"]
+    assert tests[ray.ACCEL_BRUTE] == st["sphere_tests"] and tests[ray.ACCEL_BVH] < tests[ray.ACCEL_BRUTE] / 10
+
+
+def test_bvh_ties_nested_and_degenerate_scenes(ctx, O):
+    L = ray.Lambertian((.8, .7, .6))
+    scenes = {
+        # 9 identical spheres land in different leaves: the tie must still go to index 0
+        "ties": [ray.Sphere((0, 0, -3), .5, ray.Metal((.9, .9, .9), 0.1))] * 9 + [ray.Sphere((0, -100.5, -3), 100, L)],
+        "nested": ray.DefaultScene().Objects,  # glass sphere with an inner bubble: back-face hits
+        "line": [ray.Sphere((0.01 * i, 0, -4), .3, ray.Dielectric(1.5) if i % 3 else L) for i in range(23)],
+        "one": [ray.Sphere((0, 0, -2), .7, L)],
+    }
+    for name, objs in scenes.items():
+        scene = ray.Scene(list(objs), ray.DefaultBackground())
+        for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH):
+            t = tracer(61, 33, 3, 30, seed=5, cam=ray.Camera(VerticalFoV=40.0))
+            t.Accel = accel
+            img = t.Render(scene).copy()
+            ref, _, st = O.render(oracle_flat(O, scene), oracle_cam(O, t),
+                                  O.make_params(61, 33, spp=3, max_depth=30, seed=5, num_workers=2, stream_mode=1))
+            assert np.array_equal(img, ref) and t.Stats["segments"] == st["segments"], (name, accel)
+
+
+# ---- large scene, BASELINE config 4 shape at a small image: BVH (automatic above 2048 spheres) and linear scan ------
 def test_dense_scene_10k_spheres(ctx, O):
     scene = ray.RichScene(rand.New(2), half=50)
     assert 9900 < len(scene.Objects) < 10005
-    t = tracer(48, 27, 2, 12)
-    img = t.Render(scene).copy()
     ref, _, st = O.render(O.rich_scene(2, 50), O.camera_init(48, 27, **O.RICH_CAMERA),
                           O.make_params(48, 27, spp=2, max_depth=12, seed=2, num_workers=8, stream_mode=1, fma_mode=0))
-    assert np.array_equal(img, ref) and t.Stats["segments"] == st["segments"]
+    for accel in (ray.ACCEL_AUTO, ray.ACCEL_BRUTE):
+        t = tracer(48, 27, 2, 12)
+        t.Accel = accel
+        img = t.Render(scene).copy()
+        assert np.array_equal(img, ref) and t.Stats["segments"] == st["segments"], accel
+        if accel == ray.ACCEL_AUTO:
+            assert t.Stats["sphere_tests"] < st["sphere_tests"] / 50
 
 
 # ---- full-size properties (BASELINE config 2: 1920x1080, 64 rays/pixel, depth 50) ---------------------------

@@ -12,6 +12,7 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 STREAM_REFERENCE, STREAM_PER_SAMPLE = 0, 1
 FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
+ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
@@ -39,7 +40,7 @@ class Params(C.Structure):
                 ("ray_radius", C.c_double), ("seed", C.c_uint64), ("y0", C.c_int32), ("y1", C.c_int32),
                 ("stream_mode", C.c_int32), ("num_workers", C.c_int32), ("stream_idx", C.c_int64),
                 ("precision", C.c_int32), ("split_mode", C.c_int32), ("shard_index", C.c_int32),
-                ("shard_count", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("shard_count", C.c_int32), ("accel", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):

@@ -101,6 +101,7 @@ struct Device {
     double* radius_d = nullptr; float* radius_f = nullptr;
     uint8_t* kind = nullptr; double4* params = nullptr;
     float4* fpair = nullptr; float filt_mc = 0, filt_r2max = 0;
+    BvhNode* bvh = nullptr; int* bvh_leaf_ids = nullptr; int* bvh_always = nullptr; int bvh_n_always = 0; double bvh_extent = 0;
     // work buffers (grown on demand)
     double* scratch = nullptr; size_t scratch_cap = 0;  // doubles
     uint8_t* rgba = nullptr; size_t rgba_cap = 0;       // bytes
@@ -164,6 +165,8 @@ void free_scene(Device& d) {
     cudaSetDevice(d.dev);
     cudaFree(d.geo_d); cudaFree(d.geo_f); cudaFree(d.radius_d); cudaFree(d.radius_f); cudaFree(d.kind); cudaFree(d.params);
     cudaFree(d.fpair); d.fpair = nullptr;
+    cudaFree(d.bvh); cudaFree(d.bvh_leaf_ids); cudaFree(d.bvh_always);
+    d.bvh = nullptr; d.bvh_leaf_ids = nullptr; d.bvh_always = nullptr; d.bvh_n_always = 0;
     d.geo_d = nullptr; d.geo_f = nullptr; d.radius_d = nullptr; d.radius_f = nullptr; d.kind = nullptr; d.params = nullptr;
 }
 
@@ -172,6 +175,7 @@ template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device
     DevScene<double> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
+    s.bvh = d.bvh; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
@@ -179,6 +183,7 @@ template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& 
     DevScene<float> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
     s.fpair = nullptr; s.filt_mc = 0; s.filt_r2max = 0;
+    s.bvh = nullptr; s.bvh_leaf_ids = nullptr; s.bvh_always = nullptr; s.bvh_n_always = 0; s.bvh_extent = 0;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
@@ -219,11 +224,16 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 
 template <typename T, bool FMA>
 struct TraceLaunch {
-    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false) {
+    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, bool bvh = false) {
         typedef typename Vec4T<T>::type T4;
         const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
         const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
         if constexpr (sizeof(T) == 8) {
+            if (bvh) {
+                GeoArg<T, kGeoBVH> none{};
+                launch_trace_geo<T, FMA, kGeoBVH>(d, A, S, none, tail);
+                return;
+            }
             if (filter && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
                 GeoArg<T, kGeoFilter> none{};
                 launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
@@ -246,11 +256,88 @@ struct TraceLaunch {
     }
 };
 
-void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision) {
-    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
-    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true);
-    else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data());
+void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision, int accel) {
+    const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
+    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh);
+    else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
+}
+
+// ---- host BVH build: median split on the longest centroid axis, <= 4 spheres per leaf ----------------------
+struct HostBvh {
+    std::vector<BvhNode> nodes;
+    std::vector<int> leaf_ids, always;
+    double extent = 0;
+    int max_depth = 0;
+};
+
+void bvh_bounds(const tray_scene_desc* sc, const int* ids, int n, double lo[3], double hi[3]) {
+    for (int k = 0; k < 3; k++) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
+    for (int j = 0; j < n; j++) {
+        int i = ids[j];
+        const double c[3] = {sc->cx[i], sc->cy[i], sc->cz[i]};
+        const double r = std::fabs(sc->radius[i]);
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], c[k] - r); hi[k] = std::max(hi[k], c[k] + r); }
+    }
+    for (int k = 0; k < 3; k++) {  // pad outwards: 2^-30 relative (+ tiny absolute), far above any fp64 rounding in the tests
+        double m = std::max(std::fabs(lo[k]), std::fabs(hi[k])) + 1.0;
+        lo[k] -= m * 9.4e-10; hi[k] += m * 9.4e-10;
+    }
+}
+
+int bvh_build_rec(const tray_scene_desc* sc, HostBvh& b, std::vector<int>& ids, int first, int n, int depth) {
+    int me = (int)b.nodes.size();
+    b.nodes.push_back(BvhNode{});
+    b.max_depth = std::max(b.max_depth, depth);
+    double lo[3], hi[3];
+    bvh_bounds(sc, ids.data() + first, n, lo, hi);
+    for (int k = 0; k < 3; k++) { b.nodes[me].lo[k] = lo[k]; b.nodes[me].hi[k] = hi[k]; b.extent = std::max(b.extent, std::max(std::fabs(lo[k]), std::fabs(hi[k]))); }
+    if (n <= 4) {
+        std::sort(ids.begin() + first, ids.begin() + first + n);
+        b.nodes[me].left = -((int)b.leaf_ids.size() + 1);
+        b.nodes[me].right = n;
+        b.nodes[me].axis = 0;
+        for (int j = 0; j < n; j++) b.leaf_ids.push_back(ids[first + j]);
+        return me;
+    }
+    double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (int j = 0; j < n; j++) {
+        int i = ids[first + j];
+        const double c[3] = {sc->cx[i], sc->cy[i], sc->cz[i]};
+        for (int k = 0; k < 3; k++) { clo[k] = std::min(clo[k], c[k]); chi[k] = std::max(chi[k], c[k]); }
+    }
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    const double* key = axis == 0 ? sc->cx : (axis == 1 ? sc->cy : sc->cz);
+    int half = n / 2;
+    std::nth_element(ids.begin() + first, ids.begin() + first + half, ids.begin() + first + n,
+                     [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
+    int l = bvh_build_rec(sc, b, ids, first, half, depth + 1);
+    int r = bvh_build_rec(sc, b, ids, first + half, n - half, depth + 1);
+    b.nodes[me].left = l; b.nodes[me].right = r; b.nodes[me].axis = axis;
+    return me;
+}
+
+HostBvh bvh_build(const tray_scene_desc* sc) {
+    HostBvh b;
+    int n = sc->n;
+    if (n == 0) return b;
+    // spheres much larger than the typical one (the r=1000 ground) or with non-finite data stay out of the tree
+    std::vector<double> rs(n);
+    for (int i = 0; i < n; i++) rs[i] = std::fabs(sc->radius[i]);
+    std::vector<double> sorted = rs;
+    std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
+    const double med = sorted[n / 2];
+    std::vector<int> ids;
+    for (int i = 0; i < n; i++) {
+        bool finite = std::isfinite(sc->cx[i]) && std::isfinite(sc->cy[i]) && std::isfinite(sc->cz[i]) && std::isfinite(rs[i]);
+        if (!finite || rs[i] > 16.0 * med + 1e-300) b.always.push_back(i); else ids.push_back(i);
+    }
+    if (!ids.empty()) bvh_build_rec(sc, b, ids, 0, (int)ids.size(), 1);
+    if (b.max_depth > 40) throw std::runtime_error("tray_scene_upload: BVH deeper than the traversal stack");
+    return b;
 }
 
 constexpr int kBandRows = 8;
@@ -392,12 +479,24 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
             fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nr2[0], nr2[1]);
         }
+        HostBvh hb = bvh_build(sc);
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
             free_scene(d);
             d.n = n; d.n_pad = n_pad;
             d.filt_mc = mc; d.filt_r2max = r2max;
+            d.bvh_n_always = (int)hb.always.size(); d.bvh_extent = hb.extent;
+            if (!hb.nodes.empty()) {
+                CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * hb.nodes.size()));
+                CK(cudaMemcpy(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+                CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * hb.leaf_ids.size()));
+                CK(cudaMemcpy(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice));
+            }
+            if (!hb.always.empty()) {
+                CK(cudaMalloc(&d.bvh_always, sizeof(int) * hb.always.size()));
+                CK(cudaMemcpy(d.bvh_always, hb.always.data(), sizeof(int) * hb.always.size(), cudaMemcpyHostToDevice));
+            }
             CK(cudaMalloc(&d.fpair, sizeof(float4) * n_pad));
             CK(cudaMemcpy(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
             CK(cudaMalloc(&d.geo_d, sizeof(double4) * n_pad)); CK(cudaMalloc(&d.geo_f, sizeof(float4) * n_pad));
@@ -462,6 +561,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (p->y0 < 0 || p->y1 > p->height || p->y0 > p->y1) return fail(ctx, TRAY_E_INVALID, "tray_render: bad row range");
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
     if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP64_STRICT_BRUTE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
+    if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_BVH) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
     const int rows = p->y1 - p->y0;
@@ -568,7 +668,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
                     CK(cudaEventRecord(next_event(d), d.stream));
-                    launch_trace(ctx, d, A, p->precision);
+                    launch_trace(ctx, d, A, p->precision, p->accel);
                     CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
@@ -606,7 +706,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->split_mode = p->split_mode;
         if (rgba_out) copy_out(ctx, rgba_out, stride);
         double kernel_ms = 0, trace_ms = 0;
-        unsigned long long seg = 0, exh = 0;
+        unsigned long long seg = 0, exh = 0, bvh_tests = 0;
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
@@ -619,9 +719,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             }
             kernel_ms = std::max(kernel_ms, (double)ms);
             trace_ms = std::max(trace_ms, (double)ms2);
-            unsigned long long st[3];
+            unsigned long long st[4];
             CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
-            seg += st[0]; exh += st[1];
+            seg += st[0]; exh += st[1]; bvh_tests += st[3];
         }
         ctx->have_image = true; ctx->have_hdr = true;
         ctx->rendering = false;
@@ -637,7 +737,8 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             memset(stats, 0, sizeof *stats);
             stats->paths = my_rows * (unsigned long long)p->width * (unsigned long long)p->spp;
             stats->segments = seg;
-            stats->sphere_tests = seg * (unsigned long long)ctx->devs[0].n;
+            // brute force: every Scene.Hit tests every sphere; BVH: exact tests counted by the kernel
+            stats->sphere_tests = bvh_tests ? bvh_tests : seg * (unsigned long long)ctx->devs[0].n;
             stats->depth_exhausted = exh;
             stats->kernel_ms = kernel_ms;
             stats->trace_kernel_ms = trace_ms;

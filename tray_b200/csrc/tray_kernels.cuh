@@ -56,7 +56,7 @@ template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_fl
 //                instructions take them as operands: no LDS, no vector registers for sphere data.
 //   kGeoShared : SoA table staged in shared memory, broadcast LDS.128.
 //   kGeoGlobal : read-only global loads (scenes too large for shared memory).
-enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3 };
+enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3, kGeoBVH = 4 };
 #ifndef TRAY_PARAM_GEO
 #define TRAY_PARAM_GEO 0
 #endif
@@ -117,6 +117,71 @@ __device__ __noinline__ void push_candidates(const typename Vec4T<T>::type* __re
     *ncand_io = ncand;
 }
 
+// Exact Sphere.Hit for order-independent traversal: the root the reference would accept for this sphere
+// (objects.go:90-97: near root if it is > tmin, else the far root if that is > tmin) competes with the best so far
+// by (t, id) lexicographic order, which is what the reference's "strictly closer wins" scan in index order yields.
+template <typename T, bool FMA>
+__device__ __forceinline__ void exact_test_unordered(const typename Vec4T<T>::type* __restrict__ ggeo, int id, T ox, T oy, T oz,
+                                                     T dx, T dy, T dz, T a, T& best_t, int& best) {
+    typename Vec4T<T>::type g = ggeo[id];
+    T h, c, disc;
+    sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+    if (certainly_missed(h, c, disc)) return;
+    if (disc < T(0)) return;
+    const T tmin = T(1e-6);
+    T sq = tsqrt(disc);
+    T root = (h - sq) / a;
+    if (!(root > tmin)) {
+        root = (h + sq) / a;
+        if (!(root > tmin)) return;
+    }
+    if (root < best_t || (root == best_t && id < best)) { best_t = root; best = id; }
+}
+
+// Closest hit through the BVH. Culling is conservative (padded fp64 boxes, slack on the slab comparison), so every
+// sphere the exact test could accept is reached; the result equals the linear scan bit for bit.
+template <typename T, bool FMA>
+__device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const typename Vec4T<T>::type* __restrict__ ggeo, bool has,
+                                                T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best, unsigned& ntests) {
+    if (!has) return;
+    ntests += S.bvh_n_always;
+    for (int k = 0; k < S.bvh_n_always; k++) exact_test_unordered<T, FMA>(ggeo, S.bvh_always[k], ox, oy, oz, dx, dy, dz, a, best_t, best);
+    if (!S.bvh) return;
+    const double o[3] = {(double)ox, (double)oy, (double)oz};
+    const double inv[3] = {1.0 / (double)dx, 1.0 / (double)dy, 1.0 / (double)dz};
+    // an origin absurdly far from the scene would make (lo - o) lose all its bits: then do not cull at all
+    const bool cull = fmax(fabs(o[0]), fmax(fabs(o[1]), fabs(o[2]))) < 1048576.0 * (S.bvh_extent + 1.0);
+    int stack[48];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const BvhNode nd = S.bvh[stack[--sp]];
+        if (cull) {
+            double tn = 0.0, tf = (double)best_t;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double t1 = (nd.lo[k] - o[k]) * inv[k], t2 = (nd.hi[k] - o[k]) * inv[k];
+                tn = fmax(tn, fmin(t1, t2));  // fmin/fmax drop NaNs (0*inf when the origin lies on a slab plane)
+                tf = fmin(tf, fmax(t1, t2));
+            }
+            if (!(tn <= tf * 1.000000001 + 1e-300)) continue;
+        }
+        if (nd.left < 0) {
+            const int first = -nd.left - 1;
+            ntests += nd.right;
+            for (int k = 0; k < nd.right; k++)
+                exact_test_unordered<T, FMA>(ggeo, S.bvh_leaf_ids[first + k], ox, oy, oz, dx, dy, dz, a, best_t, best);
+        } else {
+            // nearer child last on the stack (popped first) so best_t shrinks early
+            const bool neg = (nd.axis == 0 ? (double)dx : (nd.axis == 1 ? (double)dy : (double)dz)) < 0.0;
+            if (sp <= 46) {
+                stack[sp++] = neg ? nd.left : nd.right;
+                stack[sp++] = neg ? nd.right : nd.left;
+            }
+        }
+    }
+}
+
 template <typename T, bool FMA, int TPB, int MINB, int GEO>
 __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
                                                           const __grid_constant__ GeoArg<T, GEO> GP) {
@@ -149,8 +214,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     Pcg rng = pcg_new_idx(0, 0);
     int depth_left = 0, sp = 0;
     uint16_t stk[kMaxDepth];
-    unsigned long long nseg = 0;
-    unsigned nexh = 0, ndone = 0;
+    unsigned long long nseg = 0, ntests = 0;
+    unsigned nexh = 0, ndone = 0, ntests_blk = 0;
     const int n_pad = S.n_pad;
 
     for (;;) {
@@ -202,7 +267,10 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         T best_t = t_inf<T>();
         int best = -1, ncand = 0;
         unsigned mask_prev = 0;
-        if constexpr (GEO == kGeoFilter) {
+        if constexpr (GEO == kGeoBVH) {
+            bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
+            if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
+        } else if constexpr (GEO == kGeoFilter) {
             // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction) ----
             // A test is skipped only when the fp32 evaluation PROVES the strict fp64 test returns false
             // ("exact pre-filter"): with T = K1*L + K2 bounding every fp32/conversion error,
@@ -353,7 +421,9 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     }
 
     // stats: warp-reduce, one atomic per warp
+    ntests += ntests_blk;
     for (int off = 16; off > 0; off >>= 1) {
+        ntests += __shfl_down_sync(kFull, ntests, off);
         nseg += __shfl_down_sync(kFull, nseg, off);
         nexh += __shfl_down_sync(kFull, nexh, off);
         ndone += __shfl_down_sync(kFull, ndone, off);
@@ -361,6 +431,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     if (lane == 0) {
         atomicAdd(&A.stats[0], nseg);
         atomicAdd(&A.stats[1], (unsigned long long)nexh);
+        if (ntests) atomicAdd(&A.stats[3], ntests);
         if (A.progress) atomicAdd(A.progress, (unsigned long long)ndone);
     }
 }
