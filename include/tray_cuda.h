@@ -144,6 +144,14 @@ TRAY_API int tray_render(tray_ctx *ctx, const tray_camera *cam, const tray_param
 TRAY_API int tray_read_image(tray_ctx *ctx, uint8_t *rgba_out, size_t stride);
 TRAY_API int tray_read_hdr(tray_ctx *ctx, double *hdr_out);
 
+/* The interactive path after Render (main.go:119-130), on the device: scale the last rendered frame (which must be
+ * complete and resident on one device) to cols x rows2 pixels with draw.BiLinear semantics (x/image/draw, draw.Over onto
+ * a fresh image), then emit the half-block truecolor frame for a cols x rows2/2 terminal: per cell the fixed-width
+ * record ESC[48;2;RRR;GGG;BBBm ESC[38;2;RRR;GGG;BBBm U+2584 (41 bytes), per row ESC[0m LF (5 bytes).
+ * rgba_small_out (cols*rows2*4) and ansi_out may each be NULL. ansi_len receives (rows2/2)*(cols*41+5). */
+TRAY_API int tray_present(tray_ctx *ctx, int32_t cols, int32_t rows2, uint8_t *rgba_small_out, uint8_t *ansi_out, size_t ansi_cap,
+                          size_t *ansi_len, double *device_ms);
+
 /* RNG-independent parity probe: closest hit of every pixel-centre pinhole primary ray.
  * id -1 / t +Inf on a miss. Arrays are width*height (normal: x3). */
 TRAY_API int tray_first_hit(tray_ctx *ctx, const tray_camera *cam, int32_t width, int32_t height, int32_t precision,

@@ -89,6 +89,9 @@ def lib():
         _lib.oracle_ray_color.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                           C.c_int, C.c_void_p]
         _lib.oracle_set_variants.argtypes = [C.c_int, C.c_int]
+        _lib.oracle_bilinear_scale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        _lib.oracle_ansi_halfblocks.restype = C.c_size_t
+        _lib.oracle_ansi_halfblocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -259,3 +262,22 @@ def ray_color(scene, origin, direction, depth, idx=0, seed=42, fma_mode=0):
 
 def linear_to_srgb(x):
     return int(lib().oracle_linear_to_srgb(float(x)))
+
+
+def bilinear_scale(src, dw, dh):
+    """draw.BiLinear.Scale(dst, dst.Bounds(), src, src.Bounds(), draw.Over, nil) onto a fresh RGBA (main.go:122-128)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    sh, sw = src.shape[:2]
+    dst = np.zeros((dh, dw, 4), dtype=np.uint8)
+    if lib().oracle_bilinear_scale(_p(src), sw, sh, src.strides[0], dw, dh, _p(dst)) != 0:
+        raise RuntimeError("oracle_bilinear_scale failed")
+    return dst
+
+
+def ansi_halfblocks(img):
+    """Half-block truecolor frame of an (2*rows, cols, 4) image (fixed-width records, see tray_oracle.c)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h2, w = img.shape[:2]
+    out = np.zeros((h2 // 2) * (w * 41 + 5), dtype=np.uint8)
+    n = lib().oracle_ansi_halfblocks(_p(img), w, h2, _p(out))
+    return out[:n].tobytes()

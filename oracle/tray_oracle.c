@@ -786,3 +786,115 @@ EXPORT void oracle_ray_color(const oracle_scene *sc, const double o[3], const do
     v3 c = ray_color(&cx, &rng, &r, depth);
     rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
 }
+
+/* ------------------------------------------------------------------ */
+/* "Next" row 8(f)-1: the interactive path after Render (main.go:119-130) */
+/* ------------------------------------------------------------------ */
+/* golang.org/x/image/draw v0.35.0 (go.mod:11, NOT in the reference tree): BiLinear.Scale(dst, dst.Bounds(), src,
+ * src.Bounds(), draw.Over, nil) for *image.RGBA -> freshly allocated *image.RGBA (call site main.go:127).
+ * Restated from the published algorithm (Kernel scaler: separable triangle filter whose support is widened by the
+ * scale factor when shrinking; float64 intermediates in [0,1]; 16-bit premultiplied composition). PARITY UNPINNED:
+ * no golden vector for it exists in the reference (both mains are excluded from its tests). */
+typedef struct { int i, j; double inv, inv_ffff; double center, arg_scale; } bl_src;
+
+static bl_src bl_source(int x, int dw, int sw) {
+    double scale = (double)sw / (double)dw;
+    double half = 1.0, arg = 1.0;
+    if (scale > 1) { half *= scale; arg = 1 / scale; }
+    double center = ((double)x + 0.5) * scale - 0.5;
+    int i = (int)floor(center - half);
+    if (i < 0) i = 0;
+    int j = (int)ceil(center + half);
+    if (j > sw) { j = sw; if (j < i) j = i; }
+    double total = 0.0;
+    for (int c = i; c < j; c++) {
+        double t = fabs((center - (double)c) * arg);
+        if (t >= 1.0) continue;
+        double w = 1.0 - t;
+        if (w == 0) continue;
+        total += w;
+    }
+    bl_src s;
+    s.i = i; s.j = j; s.center = center; s.arg_scale = arg;
+    s.inv = 1 / total;
+    s.inv_ffff = s.inv / 0xffff;
+    return s;
+}
+static inline double bl_weight(const bl_src *s, int c) {
+    double t = fabs((s->center - (double)c) * s->arg_scale);
+    if (t >= 1.0) return 0.0;
+    return 1.0 - t;
+}
+static uint16_t bl_ftou(double f) {
+    int32_t i = (int32_t)(0xffff * f + 0.5);
+    if (i > 0xffff) return 0xffff;
+    if (i > 0) return (uint16_t)i;
+    return 0;
+}
+
+EXPORT int oracle_bilinear_scale(const uint8_t *src, int sw, int sh, size_t sstride, int dw, int dh, uint8_t *dst /* dw*dh*4, zeroed */) {
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return -1;
+    double *tmp = (double *)malloc(sizeof(double) * 4 * (size_t)dw * (size_t)sh);
+    for (int y = 0; y < sh; y++)
+        for (int x = 0; x < dw; x++) {
+            bl_src s = bl_source(x, dw, sw);
+            double p[4] = {0, 0, 0, 0};
+            for (int c = s.i; c < s.j; c++) {
+                double w = bl_weight(&s, c);
+                if (w == 0) continue;
+                const uint8_t *px = src + (size_t)y * sstride + 4 * (size_t)c;
+                for (int k = 0; k < 4; k++) p[k] += (double)((uint32_t)px[k] * 0x101) * w;
+            }
+            double *t = tmp + 4 * ((size_t)y * dw + x);
+            for (int k = 0; k < 4; k++) t[k] = p[k] * s.inv_ffff;
+        }
+    for (int x = 0; x < dw; x++)
+        for (int y = 0; y < dh; y++) {
+            bl_src s = bl_source(y, dh, sh);
+            double p[4] = {0, 0, 0, 0};
+            for (int c = s.i; c < s.j; c++) {
+                double w = bl_weight(&s, c);
+                if (w == 0) continue;
+                const double *t = tmp + 4 * ((size_t)c * dw + x);
+                for (int k = 0; k < 4; k++) p[k] += t[k] * w;
+            }
+            for (int k = 0; k < 3; k++) if (p[k] > p[3]) p[k] = p[3];
+            uint32_t q[4];
+            for (int k = 0; k < 4; k++) q[k] = bl_ftou(p[k] * s.inv);
+            uint32_t a1 = (0xffff - q[3]) * 0x101;
+            uint8_t *d = dst + 4 * ((size_t)y * dw + x);
+            for (int k = 0; k < 4; k++) d[k] = (uint8_t)(((uint32_t)d[k] * a1 / 0xffff + q[k]) >> 8);
+        }
+    free(tmp);
+    return 0;
+}
+
+/* Half-block truecolor frame (the data format ansipixels.ShowScaledImage emits, main.go:130: two image rows per
+ * terminal row, U+2584 with the upper pixel as background and the lower pixel as foreground). The exact byte
+ * stream of ansipixels is not in the reference tree; this library defines a fixed-width record so that cells can be
+ * written independently: ESC[48;2;RRR;GGG;BBBm ESC[38;2;RRR;GGG;BBBm E2 96 84 (41 bytes), rows end ESC[0m LF (5). */
+#define ANSI_CELL 41
+#define ANSI_EOL 5
+static void ansi_cell(uint8_t *o, const uint8_t *top, const uint8_t *bot) {
+    static const char hdr[2][8] = {"\x1b[48;2;", "\x1b[38;2;"};
+    const uint8_t *px[2] = {top, bot};
+    for (int h = 0; h < 2; h++) {
+        memcpy(o, hdr[h], 7); o += 7;
+        for (int k = 0; k < 3; k++) {
+            unsigned v = px[h][k];
+            *o++ = (uint8_t)('0' + v / 100); *o++ = (uint8_t)('0' + (v / 10) % 10); *o++ = (uint8_t)('0' + v % 10);
+            *o++ = k < 2 ? ';' : 'm';
+        }
+    }
+    *o++ = 0xE2; *o++ = 0x96; *o++ = 0x84;
+}
+EXPORT size_t oracle_ansi_halfblocks(const uint8_t *img, int w, int h2 /* even */, uint8_t *out) {
+    size_t n = 0;
+    for (int r = 0; r < h2 / 2; r++) {
+        for (int x = 0; x < w; x++, n += ANSI_CELL)
+            ansi_cell(out + n, img + 4 * ((size_t)(2 * r) * w + x), img + 4 * ((size_t)(2 * r + 1) * w + x));
+        memcpy(out + n, "\x1b[0m\n", ANSI_EOL);
+        n += ANSI_EOL;
+    }
+    return n;
+}

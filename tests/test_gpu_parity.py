@@ -371,3 +371,25 @@ def test_fp32_mode_reports_psnr(ctx):
     psnr = 10 * np.log10(255.0 ** 2 / mse)
     print("fp32 PSNR vs fp64: %.2f dB" % psnr)
     assert psnr > 15.0
+
+
+# ---- "next" row 8(f)-1: on-device BiLinear downscale + half-block ANSI frame (BASELINE config 5) ---------------
+@pytest.mark.parametrize("w,h,cols,rows2", [(640, 360, 160, 90), (320, 200, 79, 50), (257, 131, 64, 32), (64, 36, 64, 36)])
+def test_present_downscale_and_ansi(ctx, O, w, h, cols, rows2):
+    t = tracer(w, h, 2, 12)
+    img = t.Render(ray.RichScene(rand.New(2))).copy()
+    ansi, small, ms = ctx.present(cols, rows2)
+    want = O.bilinear_scale(img, cols, rows2)
+    assert np.array_equal(small, want)
+    assert ansi == O.ansi_halfblocks(want)
+    # decoding the frame gives the pixels back (fixed-width records)
+    rows = rows2 // 2
+    rec = np.frombuffer(ansi, dtype=np.uint8).reshape(rows, cols * 41 + 5)
+    assert bytes(rec[0, -5:]) == b"\x1b[0m\n"
+    cells = rec[:, :-5].reshape(rows, cols, 41)
+    def num(a):
+        return (a[..., 0] - 48) * 100 + (a[..., 1] - 48) * 10 + (a[..., 2] - 48)
+    top = np.stack([num(cells[..., 7 + 4 * k: 10 + 4 * k]) for k in range(3)], axis=-1)
+    bot = np.stack([num(cells[..., 26 + 4 * k: 29 + 4 * k]) for k in range(3)], axis=-1)
+    assert np.array_equal(top, small[0::2, :, :3]) and np.array_equal(bot, small[1::2, :, :3])
+    assert (cells[..., 38:] == np.array([0xE2, 0x96, 0x84], dtype=np.uint8)).all()

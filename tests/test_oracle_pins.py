@@ -270,3 +270,22 @@ def test_oracle_matches_committed_golden(O):
         assert np.array_equal(img, g[name + "_rgba"]) and np.array_equal(hdr, g[name + "_hdr"]), name
         assert st["segments"] == int(g[name + "_segments"])
     assert np.array_equal(O.rng_u64(5, 42, 32), g["rng_u64"]) and np.array_equal(O.rng_norm(5, 42, 4096), g["rng_norm"])
+
+
+# ---- "next" row 8(f)-1 restatements (third-party x/image/draw; parity unpinned, properties only) ---------------
+def test_bilinear_scale_properties(O):
+    c = np.full((90, 160, 4), 137, dtype=np.uint8)
+    c[..., 3] = 255
+    assert np.unique(O.bilinear_scale(c, 40, 30)[..., :3]).tolist() == [137]  # constants are preserved
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, (64, 96, 4), dtype=np.uint8)
+    src[..., 3] = 255
+    same = O.bilinear_scale(src, 96, 64)  # scale 1: the triangle filter degenerates to the identity
+    assert np.array_equal(same, src)
+    yy, xx = np.mgrid[0:64, 0:96]
+    smooth = np.stack([xx * 2, yy * 3, (xx + yy), np.full_like(xx, 255)], axis=-1).astype(np.uint8)
+    half = O.bilinear_scale(smooth, 48, 32).astype(int)
+    box = smooth.reshape(32, 2, 48, 2, 4).mean(axis=(1, 3))
+    assert np.abs(half[1:-1, 1:-1, :3] - box[1:-1, 1:-1, :3]).max() <= 1.0 and (half[..., 3] == 255).all()  # linear ramps survive
+    frame = O.ansi_halfblocks(half.astype(np.uint8))
+    assert len(frame) == 16 * (48 * 41 + 5) and frame.startswith(b"\x1b[48;2;") and frame.endswith(b"\x1b[0m\n")

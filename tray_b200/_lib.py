@@ -16,7 +16,7 @@ ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
-           "tray_progress", "tray_measure_peak")
+           "tray_progress", "tray_measure_peak", "tray_present")
 
 
 class TrayError(RuntimeError):
@@ -96,6 +96,8 @@ def lib():
         L.tray_first_hit.argtypes = [C.c_void_p, C.POINTER(CameraC), C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.tray_rng_dump.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_double, C.c_int32, C.c_void_p]
         L.tray_linear_to_srgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.tray_present.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                   C.POINTER(C.c_double)]
         L.tray_progress.argtypes = [C.c_void_p]
         L.tray_progress.restype = C.c_uint64
         L.tray_measure_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -846,6 +846,43 @@ int tray_linear_to_srgb(tray_ctx* ctx, const double* x, int32_t n, uint8_t* out)
     return TRAY_OK;
 }
 
+int tray_present(tray_ctx* ctx, int32_t cols, int32_t rows2, uint8_t* rgba_small_out, uint8_t* ansi_out, size_t ansi_cap,
+                 size_t* ansi_len, double* device_ms) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->have_image) return fail(ctx, TRAY_E_INVALID, "tray_present: nothing rendered");
+    if (cols <= 0 || rows2 <= 0 || (rows2 & 1)) return fail(ctx, TRAY_E_INVALID, "tray_present: cols > 0 and an even rows2 > 0 required");
+    Device& d = ctx->devs[0];
+    if (ctx->y0 != 0 || ctx->y1 != ctx->height || (int)d.local_rows.size() != ctx->height)
+        return fail(ctx, TRAY_E_UNSUPPORTED, "tray_present: needs a complete frame resident on one device (single-device context or sample split)");
+    const size_t need = (size_t)(rows2 / 2) * ((size_t)cols * kAnsiCell + kAnsiEol);
+    if (ansi_len) *ansi_len = need;
+    if (ansi_out && ansi_cap < need) return fail(ctx, TRAY_E_INVALID, "tray_present: ansi_out too small");
+    try {
+        CK(cudaSetDevice(d.dev));
+        const int sw = ctx->width, sh = ctx->height;
+        double4* tmp; uchar4* small; unsigned char* ansi;
+        CK(cudaMalloc(&tmp, sizeof(double4) * (size_t)cols * sh));
+        CK(cudaMalloc(&small, sizeof(uchar4) * (size_t)cols * rows2));
+        CK(cudaMalloc(&ansi, need));
+        cudaEvent_t a = next_event(d), b = next_event(d);
+        CK(cudaEventRecord(a, d.stream));
+        scale_x_kernel<<<dim3((cols + 127) / 128, sh), 128, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), sw, sh, cols, tmp);
+        scale_y_kernel<<<dim3((cols + 127) / 128, rows2), 128, 0, d.stream>>>(tmp, cols, sh, rows2, small);
+        ansi_kernel<<<dim3((cols + 1 + 127) / 128, rows2 / 2), 128, 0, d.stream>>>(small, cols, rows2 / 2, ansi);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b, d.stream));
+        if (ansi_out) CK(cudaMemcpyAsync(ansi_out, ansi, need, cudaMemcpyDeviceToHost, d.stream));
+        if (rgba_small_out) CK(cudaMemcpyAsync(rgba_small_out, small, sizeof(uchar4) * (size_t)cols * rows2, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (device_ms) *device_ms = ms;
+        cudaFree(tmp); cudaFree(small); cudaFree(ansi);
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
 uint64_t tray_progress(tray_ctx* ctx) {
     if (!ctx) return 0;
     if (!ctx->rendering.load()) return ctx->progress_base.load();

@@ -640,6 +640,99 @@ __global__ void __launch_bounds__(128) first_hit_kernel(DevCamera cam, DevScene<
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Next" row 8(f)-1: what tray does with the image after Render (main.go:119-130), kept on the device:
+// draw.BiLinear.Scale (x/image/draw Kernel scaler, separable triangle filter widened by the scale factor,
+// float64 intermediates, 16-bit premultiplied Over onto a fresh image) and the half-block truecolor frame.
+// ---------------------------------------------------------------------------------------------
+struct BlSrc { int i, j; double inv, inv_ffff, center, arg; };
+
+__device__ __forceinline__ double bl_weight(const BlSrc& s, int c) {
+    double t = fabs((s.center - (double)c) * s.arg);
+    return t >= 1.0 ? 0.0 : 1.0 - t;
+}
+__device__ __forceinline__ BlSrc bl_source(int x, int dw, int sw) {
+    double scale = (double)sw / (double)dw;
+    double half = 1.0, arg = 1.0;
+    if (scale > 1) { half *= scale; arg = 1 / scale; }
+    BlSrc s;
+    s.center = ((double)x + 0.5) * scale - 0.5;
+    s.arg = arg;
+    int i = (int)floor(s.center - half);
+    if (i < 0) i = 0;
+    int j = (int)ceil(s.center + half);
+    if (j > sw) { j = sw; if (j < i) j = i; }
+    s.i = i; s.j = j;
+    double total = 0.0;
+    for (int c = i; c < j; c++) total += bl_weight(s, c);  // zero weights add nothing, like the reference's `continue`
+    s.inv = 1 / total;
+    s.inv_ffff = s.inv / 65535.0;
+    return s;
+}
+__device__ __forceinline__ unsigned bl_ftou(double f) {
+    int i = (int)(65535.0 * f + 0.5);
+    return i > 0xffff ? 0xffffu : (i > 0 ? (unsigned)i : 0u);
+}
+
+__global__ void __launch_bounds__(128) scale_x_kernel(const uchar4* __restrict__ src, int sw, int sh, int dw, double4* __restrict__ tmp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= sh) return;
+    BlSrc s = bl_source(x, dw, sw);
+    double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    for (int c = s.i; c < s.j; c++) {
+        double w = bl_weight(s, c);
+        if (w == 0) continue;
+        uchar4 px = src[(size_t)y * sw + c];
+        p0 += (double)((unsigned)px.x * 0x101u) * w;
+        p1 += (double)((unsigned)px.y * 0x101u) * w;
+        p2 += (double)((unsigned)px.z * 0x101u) * w;
+        p3 += (double)((unsigned)px.w * 0x101u) * w;
+    }
+    tmp[(size_t)y * dw + x] = make_double4(p0 * s.inv_ffff, p1 * s.inv_ffff, p2 * s.inv_ffff, p3 * s.inv_ffff);
+}
+
+__global__ void __launch_bounds__(128) scale_y_kernel(const double4* __restrict__ tmp, int dw, int sh, int dh, uchar4* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    BlSrc s = bl_source(y, dh, sh);
+    double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    for (int c = s.i; c < s.j; c++) {
+        double w = bl_weight(s, c);
+        if (w == 0) continue;
+        double4 t = tmp[(size_t)c * dw + x];
+        p0 += t.x * w; p1 += t.y * w; p2 += t.z * w; p3 += t.w * w;
+    }
+    if (p0 > p3) p0 = p3;
+    if (p1 > p3) p1 = p3;
+    if (p2 > p3) p2 = p3;
+    unsigned q0 = bl_ftou(p0 * s.inv), q1 = bl_ftou(p1 * s.inv), q2 = bl_ftou(p2 * s.inv), q3 = bl_ftou(p3 * s.inv);
+    // Over onto a freshly allocated (zero) destination: dst*pa1/0xffff contributes 0
+    dst[(size_t)y * dw + x] = make_uchar4((unsigned char)(q0 >> 8), (unsigned char)(q1 >> 8), (unsigned char)(q2 >> 8), (unsigned char)(q3 >> 8));
+}
+
+constexpr int kAnsiCell = 41, kAnsiEol = 5;
+// One thread per terminal cell: ESC[48;2;RRR;GGG;BBBm ESC[38;2;RRR;GGG;BBBm U+2584 ; thread x == w writes ESC[0m LF.
+__global__ void __launch_bounds__(128) ansi_kernel(const uchar4* __restrict__ img, int w, int rows, unsigned char* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (x > w || r >= rows) return;
+    unsigned char* o = out + (size_t)r * ((size_t)w * kAnsiCell + kAnsiEol) + (size_t)x * kAnsiCell;
+    if (x == w) { o[0] = 0x1b; o[1] = '['; o[2] = '0'; o[3] = 'm'; o[4] = '\n'; return; }
+    uchar4 px[2] = {img[(size_t)(2 * r) * w + x], img[(size_t)(2 * r + 1) * w + x]};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        o[0] = 0x1b; o[1] = '['; o[2] = h == 0 ? '4' : '3'; o[3] = '8'; o[4] = ';'; o[5] = '2'; o[6] = ';';
+        o += 7;
+        unsigned v[3] = {px[h].x, px[h].y, px[h].z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            o[0] = (unsigned char)('0' + v[k] / 100); o[1] = (unsigned char)('0' + (v[k] / 10) % 10); o[2] = (unsigned char)('0' + v[k] % 10);
+            o[3] = k < 2 ? ';' : 'm';
+            o += 4;
+        }
+    }
+    o[0] = 0xE2; o[1] = 0x96; o[2] = 0x84;
+}
+
 // Generator parity probe (single thread).
 __global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long long seed, double radius, int n, double* out) {
     __shared__ ZigTables zig;

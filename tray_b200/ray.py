@@ -288,6 +288,18 @@ class Context:
         _lib.check(self.handle, self._L.tray_linear_to_srgb(self.handle, x.ctypes.data_as(C.c_void_p), len(x), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def present(self, cols, rows2, want_image=True):
+        """main.go:119-130 on the device: BiLinear downscale of the last frame to cols x rows2 and the half-block ANSI frame
+        for a cols x rows2/2 terminal. Returns (ansi bytes, small image or None, device ms)."""
+        n = C.c_size_t()
+        ms = C.c_double()
+        small = np.zeros((rows2, cols, 4), dtype=np.uint8) if want_image else None
+        cap = (rows2 // 2) * (cols * 41 + 5)
+        buf = np.zeros(cap, dtype=np.uint8)
+        _lib.check(self.handle, self._L.tray_present(self.handle, cols, rows2, small.ctypes.data_as(C.c_void_p) if want_image else None,
+                                                     buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(ms)))
+        return buf[:n.value].tobytes(), small, ms.value
+
     def progress(self):
         return int(self._L.tray_progress(self.handle))
 
