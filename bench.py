@@ -309,6 +309,23 @@ def run_ours(args):
             alts.append({"precision": name, "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
                          "roofline": {"bound": "fp64", "achieved": a_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": a_tf / peak_tf},
                          "note": notes[name]})
+        # fp32 fast path: throughput + PSNR of its 8-bit image against the fp64 image (same streams)
+        if world == 1:
+            p3 = tr._params(0, h)
+            p3.precision = ray.FP32
+            img64 = np.zeros((h, w, 4), dtype=np.uint8)
+            img32 = np.zeros((h, w, 4), dtype=np.uint8)
+            ctx.render(cam_c, params, img64)
+            ctx.render(cam_c, p3, img32)
+            f_ms, f_paths = 0.0, 0
+            for _ in range(args.steps):
+                st3 = ctx.render(cam_c, p3, None)
+                f_ms += st3["kernel_ms"]; f_paths += st3["paths"]
+            mse = float(((img64[:, :, :3].astype(np.float64) - img32[:, :, :3].astype(np.float64)) ** 2).mean())
+            alts.append({"precision": "fp32", "value": f_paths / (f_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+                         "psnr_db_vs_fp64": (10 * np.log10(255.0 ** 2 / mse)) if mse > 0 else None,
+                         "pixels_within_1lsb_frac": float((np.abs(img64.astype(np.int16) - img32.astype(np.int16)).max(axis=2) <= 1).mean()),
+                         "note": "float32 arithmetic end to end (same RNG streams, FrontEpsilon 1e-3 instead of 1e-6); no parity claim"})
 
     # ---- end-to-end leg: host buffers, scene H2D + image D2H inside the timed region ----
     interactive = workload == "config5" and world == 1  # tray's OnResize body: Render + downscale + ANSI frame (main.go:89-137)

@@ -71,7 +71,7 @@ template <typename T> struct GeoArg<T, kGeoParam> { typename Vec4T<T>::type g[kP
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                    T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
-    const T tmin = T(1e-6);
+    const T tmin = front_epsilon<T>();
     for (int k = 0; k < ncand; k++) {
         int id = cand[k * TPB];
         typename Vec4T<T>::type g = ggeo[id];
@@ -128,7 +128,7 @@ __device__ __forceinline__ void exact_test_unordered(const typename Vec4T<T>::ty
     sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
     if (certainly_missed(h, c, disc)) return;
     if (disc < T(0)) return;
-    const T tmin = T(1e-6);
+    const T tmin = front_epsilon<T>();
     T sq = tsqrt(disc);
     T root = (h - sq) / a;
     if (!(root > tmin)) {
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(128) first_hit_kernel(DevCamera cam, DevScene<
         typename Vec4T<T>::type g = S.geo[i];
         T h, c, disc, root;
         sphere_terms<T, FMA>(O.x, O.y, O.z, D.x, D.y, D.z, a, g.x, g.y, g.z, g.w, h, c, disc);
-        if (sphere_root<T>(h, a, disc, T(1e-6), bt, root)) { bt = root; b = i; }
+        if (sphere_root<T>(h, a, disc, front_epsilon<T>(), bt, root)) { bt = root; b = i; }
     }
     id[p] = b;
     t[p] = (double)bt;
