@@ -11,6 +11,10 @@ if [ "$1" = "ncu" ]; then
   $CMD > gpurun_out/plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
   $CMD > gpurun_out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 4 -c 2 -f -o gpurun_out/prof_trace $CMD > gpurun_out/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 4 -c 1 -f -o gpurun_out/prof_trace $CMD > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log
+  CMDB="$CMD --precision fp64-brute"
+  $CMDB > gpurun_out/plain3.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 4 -c 1 -f -o gpurun_out/prof_trace_brute $CMDB > gpurun_out/ncu_full_brute.log 2>&1
+  tail -2 gpurun_out/ncu_full_brute.log
 fi

@@ -29,7 +29,9 @@ with open(os.path.join(P, tag + "_launch_summary.txt"), "w") as f:
         f.write("%-70s %6d %12.3f %6.1f%%\n" % (k, a[0], a[1], 100 * a[1] / tot))
 
 # 2. full capture of the trace kernel -> selected raw metrics
-rep = os.path.join(G, "prof_trace.ncu-rep")
+which = sys.argv[2] if len(sys.argv) > 2 else "prof_trace"
+suffix = "" if which == "prof_trace" else "_" + which.replace("prof_trace_", "")
+rep = os.path.join(G, which + ".ncu-rep")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, u = rr[0], rr[1]
@@ -45,7 +47,7 @@ keep = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__cycles_active.avg", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum", "sm__sass_thread_inst_executed_op_dmul_pred_on.sum",
         "sm__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
-with open(os.path.join(P, tag + "_trace_kernel_metrics.csv"), "w") as f:
+with open(os.path.join(P, tag + "_trace_kernel%s_metrics.csv" % suffix), "w") as f:
     f.write("launch_id,kernel,metric,value,unit\n")
     for r in rr[2:]:
         for i, name in enumerate(h):
@@ -57,7 +59,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 tmp = os.path.join(G, "src.csv")
 open(tmp, "w").write(src)
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), tmp], capture_output=True, text=True).stdout
-open(os.path.join(P, tag + "_trace_kernel_source_summary.txt"), "w").write(
+open(os.path.join(P, tag + "_trace_kernel%s_source_summary.txt" % suffix), "w").write(
     "ncu --set full --import-source on, source page of tray::trace_kernel (first profiled launch)\n\n" + out)
 print(open(os.path.join(P, tag + "_launch_summary.txt")).read())
 print(out[:1500])
