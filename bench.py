@@ -187,7 +187,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from tray_b200 import ray, rand, _lib
+    from tray_b200 import ray, rand, _lib, multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +211,8 @@ def run_ours(args):
     tr = ray.New(w, h)
     tr.Camera = ray.RichSceneCamera()
     tr.MaxDepth, tr.NumRaysPerPixel, tr.Seed, tr.Precision = depth, spp, SEED, precision
-    tr.ShardIndex, tr.ShardCount = (rank, world) if world > 1 else (0, 0)
+    split_samples = args.split == "samples" and world > 1
+    tr.ShardIndex, tr.ShardCount = (rank, world) if (world > 1 and not split_samples) else (0, 0)
     tr.Context = ctx
     tr._prepare(scene)  # Tracer.Render's defaulting: default background, Camera.Initialize (ray/tracer.go:49-83)
     flat = scene.flatten()
@@ -219,6 +220,9 @@ def run_ours(args):
     ctx.upload(flat)
     cam_c = tr.to_c()
     params = tr._params(0, h)
+    if split_samples:  # rank r traces samples s == r (mod world) of every pixel; sums reduced to rank 0 with NCCL
+        params.sample_offset, params.sample_stride, params.sample_count = multi.sample_subset(spp, rank, world)
+        params.sums_mode = ray.SUMS_OVERWRITE
 
     # shared host image for the e2e leg (each rank writes its own row bands; no collective)
     if world > 1:
@@ -252,6 +256,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    sums_t = [None]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def exchange(out_img=None):
+        """Sample split: the one exchange step -- sum-reduce of the fp64 colour sums to rank 0 (NCCL over NVLink), then
+        1/N + sRGB on rank 0. Returns the device time of the reduce on torch's stream (CUDA events)."""
+        if sums_t[0] is None:
+            ptr, n = ctx.device_sums()
+            sums_t[0] = torch.as_tensor(multi._DeviceBuffer(ptr, n), device=torch.device("cuda", local_rank))
+        ev[0].record()
+        dist.reduce(sums_t[0], dst=0, op=dist.ReduceOp.SUM)
+        ev[1].record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if rank == 0:
+            ctx.resolve_sums(spp, out_img)
+        return ev[0].elapsed_time(ev[1]) + (time.perf_counter() - t0) * 1e3
+
     peak_tf, _ = ctx.measure_peak(0)  # DFMA issue-bound peak of this GPU, measured live
     peak_strict_tf, _ = ctx.measure_peak(1)
     peak_f32_tf, _ = ctx.measure_peak(2)
@@ -259,16 +281,22 @@ def run_ours(args):
     # ---- device-resident leg ----
     for _ in range(max(args.warmup, 3)):  # timing rules: at least 3 warm-up steps
         ctx.render(cam_c, params, None)
+        if split_samples:
+            exchange()
     sampler = ClockSampler(local_rank)
     sync_all()
     sampler.start()
     wall0 = time.perf_counter()
     dev_ms, trace_ms, launches, segments, paths, trace_launches, sphere_tests = 0.0, 0.0, 0, 0, 0, 0, 0
+    exchange_ms = 0.0
     for _ in range(args.steps):
         flush_buf.zero_()  # L2 flush between timed iterations (outside the event-timed kernels)
         torch.cuda.synchronize()
         st = ctx.render(cam_c, params, None)
         dev_ms += st["kernel_ms"]; trace_ms += st["trace_kernel_ms"]; launches += st["launches"]
+        if split_samples:
+            xms = exchange()
+            dev_ms += xms; exchange_ms += xms; launches += 1
         segments += st["segments"]; paths += st["paths"]; trace_launches += st["launches"] // 2; sphere_tests += st["sphere_tests"]
     sync_all()
     wall_ms = (time.perf_counter() - wall0) * 1e3
@@ -290,7 +318,7 @@ def run_ours(args):
 
     # ---- the other fp64 kernels, reported beside the default (same steps, device-resident) ----
     alts = []
-    if args.precision == "fp64" and not args.no_alt:
+    if args.precision == "fp64" and not args.no_alt and not split_samples:
         notes = {"fp64-brute": "same strict arithmetic, every test on the FP64 pipe (no pre-filter): 17 FP64 instructions per 18-flop test, "
                                "structural ceiling 0.529 of the DFMA peak",
                  "fp64-fma": "Sphere.Hit discriminant with fused multiply-add (11 FP64 instructions/test, ceiling 0.818), no pre-filter; image "
@@ -339,6 +367,9 @@ def run_ours(args):
             st_ = ctx.render(cam_c, params, None)                       # frame stays in HBM
             frame, _, _ = ctx.present(term_cols, term_rows * 2, want_image=False)  # BiLinear s=4 + half-block ANSI on device
             ansi_bytes = len(frame)
+        elif split_samples:
+            st_ = ctx.render(cam_c, params, None)
+            exchange(host_img)
         else:
             st_ = ctx.render(cam_c, params, host_img)
         return st_
@@ -357,7 +388,7 @@ def run_ours(args):
     h2d = sum(flat[k].nbytes for k in ("cx", "cy", "cz", "r", "kind", "params")) + 48 + \
         __import__("ctypes").sizeof(_lib.CameraC) + __import__("ctypes").sizeof(_lib.Params)
     my_rows = st["paths"] // (w * spp)
-    d2h = int(ansi_bytes) if interactive else int(my_rows * w * 4)
+    d2h = int(ansi_bytes) if interactive else (int(h * w * 4) if split_samples else int(my_rows * w * 4))
 
     # ---- CPU baseline + parity spot check (rank 0, N=1 only) ----
     cpu_baseline, parity = None, None
@@ -383,7 +414,7 @@ def run_ours(args):
             "wall_ms_per_step": wall_ms / args.steps,
             "config": {"workload": workload, "desc": desc, "width": w, "height": h, "rays_per_pixel": spp, "max_depth": depth,
                        "seed": SEED, "spheres": n_spheres, "precision": args.precision, "streams": "per-sample",
-                       "parallelism": "tiles%d" % world if world > 1 else "1gpu",
+                       "parallelism": ("samples%d+nccl_reduce" if split_samples else "tiles%d") % world if world > 1 else "1gpu",
                        "l2": "256 MiB memset between timed steps (L2 flush); working set is 31 kB of spheres in shared memory"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "power_w_max": clocks.get("power_w_max"), "samples": clocks["samples"]},
@@ -413,6 +444,9 @@ def run_ours(args):
                                  "is ~30 B/path of scratch; tensor cores do not apply"},
             "segments_per_path": all_segments / all_paths,
         }
+        if split_samples:
+            line["exchange"] = {"collective": "NCCL reduce(sum) to rank 0 + resolve", "bytes": int(w) * h * 24, "ms_per_step": exchange_ms / args.steps,
+                                "note": "fp64 colour sums (w*h*3 doubles) reduced in place on the library's device buffer; rank 0's time"}
         if interactive:
             line["keypress_latency_ms"] = e2e_ms / args.steps
             line["interactive"] = {"terminal": "%dx%d" % (term_cols, term_rows), "supersample": 4, "ansi_frame_bytes": int(ansi_bytes),
@@ -446,6 +480,8 @@ def main():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp64-brute", "fp64-fma", "fp32"],
                     help="fp64 = strict Go/amd64 semantics with the exact fp32 pre-filter (default); fp64-brute = same, all tests in fp64; "
                          "fp64-fma = fused discriminant; fp32 = fast path")
+    ap.add_argument("--split", default="tiles", choices=["tiles", "samples"],
+                    help="N>1 partitioning: interleaved row bands (no collective, default) or sample split + NCCL sum-reduce")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

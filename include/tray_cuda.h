@@ -15,6 +15,7 @@
  *                         Sphere ray/objects.go:75-79, Lambertian/Metal/Dielectric ray/materials.go:9-44
  *   tray_camera        <- Camera after Initialize  ray/camera.go:9-39,43-105 (Initialize stays on the host)
  *   tray_first_hit     <- Scene.Hit + Sphere.Hit   ray/objects.go:37-46,81-104 (parity probe, RNG-free)
+ *   tray_resolve_sums  <- the tail of RenderLines   ray/tracer.go:145-152 (colorSum * 1/N, ToSRGBA, Pix store)
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
  *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
  */
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TRAY_ABI_VERSION 1
+#define TRAY_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TRAY_API __attribute__((visibility("default")))
@@ -72,6 +73,11 @@ extern "C" {
 #define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */
 #define TRAY_SPLIT_SAMPLES 1 /* each GPU renders samples s == g (mod G); partial sums reduced over NVLink */
 
+/* sample-subset modes (tray_params.sums_mode) */
+#define TRAY_SUMS_OFF 0        /* classic: all samples, mean, sRGB image */
+#define TRAY_SUMS_OVERWRITE 1  /* sums := sum over this call's samples */
+#define TRAY_SUMS_ACCUMULATE 2 /* sums := previous sums continued with this call's samples (same geometry required) */
+
 typedef struct tray_ctx tray_ctx;
 
 /* Flattened scene: SoA over spheres, in Scene.Objects order (ties resolve to the lowest index). */
@@ -109,7 +115,15 @@ typedef struct {
                              row bands b with b % shard_count == shard_index (0,1 or 0,0 = everything);
                              rows of other shards in the output are left untouched */
     int32_t accel;        /* TRAY_ACCEL_*: closest-hit structure (0 = automatic) */
-    int32_t reserved[4];
+    /* Sample subsets (TRAY_SUMS_* != OFF, per-sample streams only): this call traces the samples
+     * s = sample_offset + j*sample_stride, j in [0,sample_count), of every pixel and leaves the RAW colour sums
+     * (colorSum of ray/tracer.go:143, before the 1/N) in the context instead of an image; tray_resolve_sums turns
+     * them into pixels. Used for (a) multi-process sample split: rank g of G passes offset g, stride G, reduces the
+     * sums with NCCL (tray_device_sums exposes the device buffer) and the root resolves; (b) progressive refinement
+     * (camera navigation, main.go:143-163): consecutive slices offset k0, stride 1 with TRAY_SUMS_ACCUMULATE continue
+     * the sum in sample order, so the image after the last slice is bit-identical to the one-shot render. */
+    int32_t sample_offset, sample_stride, sample_count;
+    int32_t sums_mode;    /* TRAY_SUMS_* */
 } tray_params;
 
 typedef struct {
@@ -143,6 +157,15 @@ TRAY_API int tray_render(tray_ctx *ctx, const tray_camera *cam, const tray_param
 /* Copies the last rendered image / linear-HDR means (w*h*3 doubles, colorSum*(1/N) before sRGB). */
 TRAY_API int tray_read_image(tray_ctx *ctx, uint8_t *rgba_out, size_t stride);
 TRAY_API int tray_read_hdr(tray_ctx *ctx, double *hdr_out);
+
+/* Sample-subset renders (tray_params.sums_mode != 0). tray_device_sums returns the DEVICE pointer of the raw colour sums of
+ * the last such render (rows_rendered*width*3 doubles, row-major over the rows this context rendered; single-device
+ * contexts only; valid until the next render) so that a caller can reduce it across processes in place (NCCL).
+ * tray_resolve_sums computes pixel = ToSRGBA(sum * (1/n_samples)) (ray/tracer.go:145-152) for the rows this context
+ * rendered; n_samples 0 = the number of samples accumulated by this context so far. The sums stay untouched.
+ * The caller must have synchronised any stream of its own that wrote the sums. rgba_out may be NULL. */
+TRAY_API int tray_device_sums(tray_ctx *ctx, double **device_ptr, uint64_t *n_doubles);
+TRAY_API int tray_resolve_sums(tray_ctx *ctx, uint64_t n_samples, uint8_t *rgba_out, size_t stride);
 
 /* The interactive path after Render (main.go:119-130), on the device: scale the last rendered frame (which must be
  * complete and resident on one device) to cols x rows2 pixels with draw.BiLinear semantics (x/image/draw, draw.Over onto

@@ -74,6 +74,8 @@ def lib():
         _lib.oracle_render_sampled_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib.oracle_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
+        _lib.oracle_sample_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+        _lib.oracle_resolve_sums.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p]
         _lib.oracle_camera_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.oracle_rng_u64.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _lib.oracle_rng_f64.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -193,6 +195,29 @@ def render_sampled_rows(scene, cam, params, row_step, row_offset, threads, rgba=
     if rc != 0:
         raise RuntimeError("oracle_render_sampled_rows failed")
     return rgba, st.as_dict()
+
+
+def sample_sums(scene, cam, params, y0, y1, s_off, s_stride, s_count, sums=None):
+    """Raw colour sums of a sample subset (per-sample streams); `sums` given = continue them (progressive slices)."""
+    acc = sums is not None
+    if sums is None:
+        sums = np.zeros((y1 - y0, params.width, 3))
+    st = Stats()
+    sc = scene.c()
+    rc = lib().oracle_sample_sums(C.byref(sc), C.byref(cam), C.byref(params), y0, y1, s_off, s_stride, s_count, int(acc),
+                                  _p(sums), C.byref(st))
+    if rc != 0:
+        raise RuntimeError("oracle_sample_sums failed")
+    return sums, st.as_dict()
+
+
+def resolve_sums(sums, n_samples):
+    """ToSRGBA(sum * (1/n_samples)) per pixel (ray/tracer.go:145-152)."""
+    sums = np.ascontiguousarray(sums, dtype=np.float64)
+    rgba = np.zeros(sums.shape[:-1] + (4,), dtype=np.uint8)
+    if lib().oracle_resolve_sums(_p(sums), sums.size // 3, n_samples, _p(rgba)) != 0:
+        raise RuntimeError("oracle_resolve_sums failed")
+    return rgba
 
 
 def first_hit(scene, cam, width, height, fma_mode=0):

@@ -610,6 +610,40 @@ EXPORT int oracle_render_sampled_rows(const oracle_scene *sc, const oracle_camer
     return 0;
 }
 
+/* Sample subsets (per-sample streams): raw colour sums (colorSum of ray/tracer.go:143, before the 1/N) over the samples
+ * s = s_off + j*s_stride, j < s_count, of rows [y0,y1), row-major from row y0. accumulate != 0 continues the sums already
+ * in `sums` (same running sum as the one-shot loop when the slices are consecutive). Checker for tray_render's sums modes. */
+EXPORT int oracle_sample_sums(const oracle_scene *sc, const oracle_camera *cam, const oracle_params *p, int y0, int y1,
+                              int s_off, int s_stride, int s_count, int accumulate, double *sums, oracle_stats *stats) {
+    if (!sc || !cam || !p || !sums || s_stride < 1 || s_count < 0 || s_off < 0) return -1;
+    ctx_t cx = {sc, p->fma_mode, {0, 0, 0, 0, 0}};
+    for (int y = y0; y < y1; y++)
+        for (int x = 0; x < p->width; x++) {
+            double *h = sums + 3 * ((size_t)(y - y0) * p->width + x);
+            v3 sum = accumulate ? V(h[0], h[1], h[2]) : V(0, 0, 0);
+            for (int j = 0; j < s_count; j++) {
+                uint64_t s = (uint64_t)s_off + (uint64_t)j * (uint64_t)s_stride;
+                uint64_t idx = ((uint64_t)y * (uint64_t)p->width + (uint64_t)x) * (uint64_t)p->spp + s;
+                rng_t rng = rng_new_idx(idx, p->seed);
+                sum = v_add(sum, trace_sample(&cx, cam, p, &rng, x, y));
+            }
+            h[0] = sum.x; h[1] = sum.y; h[2] = sum.z;
+        }
+    if (stats) *stats = cx.st;
+    return 0;
+}
+/* pixel = ToSRGBA(sum * (1/n_samples)) (ray/tracer.go:145-152) */
+EXPORT int oracle_resolve_sums(const double *sums, size_t n_pixels, uint64_t n_samples, uint8_t *rgba) {
+    if (!sums || !rgba || !n_samples) return -1;
+    double div = 1.0 / (double)n_samples;
+    for (size_t k = 0; k < n_pixels; k++) {
+        v3 c = v_smul(V(sums[3 * k], sums[3 * k + 1], sums[3 * k + 2]), div);
+        rgba[4 * k] = oracle_linear_to_srgb(c.x); rgba[4 * k + 1] = oracle_linear_to_srgb(c.y);
+        rgba[4 * k + 2] = oracle_linear_to_srgb(c.z); rgba[4 * k + 3] = 255;
+    }
+    return 0;
+}
+
 /* Tracer.RenderLines(idx, yStart, yEnd, scene) (ray/tracer.go:120): rows outside stay untouched. */
 EXPORT int oracle_render_lines(const oracle_scene *sc, const oracle_camera *cam, const oracle_params *p,
                                int idx, int y0, int y1, uint8_t *rgba, size_t stride, double *hdr, oracle_stats *stats) {

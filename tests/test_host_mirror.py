@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert getattr(L, name) is not None
     L.tray_abi_version.restype = ctypes.c_int
-    assert L.tray_abi_version() == 1
+    assert L.tray_abi_version() == int(re.search(r'#define TRAY_ABI_VERSION (\d+)', hdr).group(1)) >= 2
 
 
 def test_ctypes_structs_match_the_c_header():
@@ -38,6 +38,7 @@ int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(tray_scene_desc), sizeof(tray_camera), sizeof(tray_params), sizeof(tray_stats));
   printf("%zu %zu %zu %zu %zu\n", offsetof(tray_params, seed), offsetof(tray_params, stream_idx), offsetof(tray_params, precision),
          offsetof(tray_params, shard_index), offsetof(tray_scene_desc, bg_a));
+  printf("%zu %zu\n", offsetof(tray_params, sample_offset), offsetof(tray_params, sums_mode));
   printf("%zu %zu\n", offsetof(tray_stats, kernel_ms), offsetof(tray_stats, trace_kernel_ms));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
@@ -50,6 +51,7 @@ int main(void) {
     P, S, St = _lib.Params, _lib.SceneDesc, _lib.Stats
     want = [ctypes.sizeof(S), ctypes.sizeof(_lib.CameraC), ctypes.sizeof(P), ctypes.sizeof(St),
             P.seed.offset, P.stream_idx.offset, P.precision.offset, P.shard_index.offset, S.bg_a.offset,
+            P.sample_offset.offset, P.sums_mode.offset,
             St.kernel_ms.offset, St.trace_kernel_ms.offset]
     assert got == want
 

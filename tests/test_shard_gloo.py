@@ -46,3 +46,42 @@ def test_two_rank_tile_sharding(tmp_path, O):
     full, _, _ = O.render(O.rich_scene(2), O.camera_init(w, h, **O.RICH_CAMERA),
                           O.make_params(w, h, spp=2, max_depth=10, seed=2, num_workers=1, stream_mode=1))
     assert np.array_equal(got, full)
+
+
+def _split_worker(rank, world, port, out, w, h, spp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from tray_b200 import multi
+    sc = O.rich_scene(2)
+    cam = O.camera_init(w, h, **O.RICH_CAMERA)
+    p = O.make_params(w, h, spp=spp, max_depth=10, seed=2, stream_mode=1)
+    off, stride, count = multi.sample_subset(spp, rank, world)
+    sums, st = O.sample_sums(sc, cam, p, 0, h, off, stride, count)   # the oracle stands in for tray_render(sums_mode)
+    t = torch.from_numpy(sums)
+    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)                       # the one exchange step of sample-split mode
+    n = torch.tensor([float(st["paths"])], dtype=torch.float64)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    assert n.item() == w * h * spp
+    if rank == 0:
+        np.save(out, O.resolve_sums(t.numpy(), spp))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sample_split(tmp_path, O):
+    """Sample-split host logic (tray_b200/multi.py): rank r takes samples s == r (mod world), sums are reduced to rank 0,
+    which resolves. Same samples as the one-shot render, different summation order: within 1 LSB."""
+    from tray_b200 import multi
+    w, h, world, spp = 40, 23, 2, 7
+    taken = sorted(off + j * st for r in range(world) for off, st, c in [multi.sample_subset(spp, r, world)] for j in range(c))
+    assert taken == list(range(spp))
+    out = str(tmp_path / "img.npy")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_split_worker, args=(world, port, out, w, h, spp), nprocs=world, join=True)
+    got = np.load(out)
+    full, _, _ = O.render(O.rich_scene(2), O.camera_init(w, h, **O.RICH_CAMERA),
+                          O.make_params(w, h, spp=spp, max_depth=10, seed=2, num_workers=1, stream_mode=1))
+    d = np.abs(got.astype(int) - full.astype(int)).max(axis=2)
+    assert d.max() <= 1 and (d == 0).mean() > 0.99

@@ -13,10 +13,11 @@ STREAM_REFERENCE, STREAM_PER_SAMPLE = 0, 1
 FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
+SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
-           "tray_progress", "tray_measure_peak", "tray_present")
+           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums")
 
 
 class TrayError(RuntimeError):
@@ -40,7 +41,8 @@ class Params(C.Structure):
                 ("ray_radius", C.c_double), ("seed", C.c_uint64), ("y0", C.c_int32), ("y1", C.c_int32),
                 ("stream_mode", C.c_int32), ("num_workers", C.c_int32), ("stream_idx", C.c_int64),
                 ("precision", C.c_int32), ("split_mode", C.c_int32), ("shard_index", C.c_int32),
-                ("shard_count", C.c_int32), ("accel", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("shard_count", C.c_int32), ("accel", C.c_int32), ("sample_offset", C.c_int32), ("sample_stride", C.c_int32),
+                ("sample_count", C.c_int32), ("sums_mode", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -98,6 +100,8 @@ def lib():
         L.tray_linear_to_srgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.tray_present.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                    C.POINTER(C.c_double)]
+        L.tray_device_sums.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.tray_resolve_sums.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
         L.tray_progress.argtypes = [C.c_void_p]
         L.tray_progress.restype = C.c_uint64
         L.tray_measure_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -147,6 +147,9 @@ struct tray_ctx {
     int width = 0, height = 0, y0 = 0, y1 = 0;
     bool have_image = false, have_hdr = false;
     int split_mode = 0;
+    bool hdr_is_sums = false;          // last render left raw colour sums (sums_mode != 0)
+    uint64_t sums_samples = 0;         // samples per pixel accumulated in them
+    int sums_key[6] = {0, 0, 0, 0, 0, 0};  // geometry the sums belong to (w, h, y0, y1, shard_index, shard_count)
     std::atomic<uint64_t> progress_base{0};
     std::atomic<int> progress_spp{1};
     std::atomic<bool> rendering{false};
@@ -564,6 +567,10 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_BVH) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
+    if (p->sums_mode < TRAY_SUMS_OFF || p->sums_mode > TRAY_SUMS_ACCUMULATE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad sums_mode");
+    if (p->sums_mode != TRAY_SUMS_OFF && p->stream_mode != TRAY_STREAM_PER_SAMPLE)
+        return fail(ctx, TRAY_E_INVALID, "tray_render: sample subsets need per-sample streams");
+    const bool subset = p->sums_mode != TRAY_SUMS_OFF;
     const int rows = p->y1 - p->y0;
     const int G = (int)ctx->devs.size();
     int launches = 0;
@@ -621,6 +628,20 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             // ---- throughput mode: per-sample streams, persistent megakernel ----
             const bool split_samples = (p->split_mode == TRAY_SPLIT_SAMPLES) && G > 1;
             if (split_samples && ext_count > 1) throw std::runtime_error("tray_render: sample split cannot be combined with external shards");
+            if (subset) {
+                if (split_samples) throw std::runtime_error("tray_render: sums_mode cannot be combined with the in-context sample split");
+                if (p->sample_stride < 1 || p->sample_count < 1 || p->sample_offset < 0 ||
+                    (long long)p->sample_offset + (long long)(p->sample_count - 1) * p->sample_stride >= (long long)p->spp)
+                    throw std::runtime_error("tray_render: sample subset out of range (need offset + (count-1)*stride < spp)");
+                const int key[6] = {p->width, p->height, p->y0, p->y1, ext_index, ext_count};
+                if (p->sums_mode == TRAY_SUMS_ACCUMULATE) {
+                    if (!ctx->hdr_is_sums || memcmp(key, ctx->sums_key, sizeof key) != 0)
+                        throw std::runtime_error("tray_render: TRAY_SUMS_ACCUMULATE needs sums of the same geometry from a previous TRAY_SUMS_* render");
+                } else {
+                    ctx->sums_samples = 0;
+                }
+                memcpy(ctx->sums_key, key, sizeof key);
+            }
             for (int g = 0; g < G; g++) {
                 Device& d = ctx->devs[g];
                 CK(cudaSetDevice(d.dev));
@@ -636,6 +657,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     stride_s = G; offset_s = g;
                     spp_local = p->spp > g ? (p->spp - g + G - 1) / G : 0;
                 }
+                if (subset) { stride_s = p->sample_stride; offset_s = p->sample_offset; spp_local = p->sample_count; }
                 CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
                 grow(d.rgba, d.rgba_cap, std::max<size_t>(n_pixels * 4, 4));
                 grow(d.hdr, d.hdr_cap, std::max<size_t>(n_pixels * 3, 3));
@@ -672,7 +694,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
-                    R.inv_spp = 1.0 / (double)p->spp; R.partial = split_samples ? 1 : 0;
+                    R.inv_spp = 1.0 / (double)p->spp; R.partial = subset ? p->sums_mode : (split_samples ? 1 : 0);
                     R.rgba = d.rgba; R.hdr = d.hdr; R.srgb_thr = d.srgb_thr;
                     resolve_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d.stream>>>(R);
                     CK(cudaGetLastError());
@@ -704,7 +726,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             }
         }
         ctx->split_mode = p->split_mode;
-        if (rgba_out) copy_out(ctx, rgba_out, stride);
+        if (rgba_out && !subset) copy_out(ctx, rgba_out, stride);
         double kernel_ms = 0, trace_ms = 0;
         unsigned long long seg = 0, exh = 0, bvh_tests = 0;
         for (Device& d : ctx->devs) {
@@ -723,7 +745,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
             seg += st[0]; exh += st[1]; bvh_tests += st[3];
         }
-        ctx->have_image = true; ctx->have_hdr = true;
+        ctx->have_image = !subset; ctx->have_hdr = true;
+        ctx->hdr_is_sums = subset;
+        if (subset) ctx->sums_samples += (uint64_t)p->sample_count;
         ctx->rendering = false;
         unsigned long long my_rows = 0;
         if (p->stream_mode == TRAY_STREAM_REFERENCE || (p->split_mode == TRAY_SPLIT_SAMPLES && G > 1)) {
@@ -735,7 +759,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->progress_base = my_rows * (unsigned long long)p->width;
         if (stats) {
             memset(stats, 0, sizeof *stats);
-            stats->paths = my_rows * (unsigned long long)p->width * (unsigned long long)p->spp;
+            stats->paths = my_rows * (unsigned long long)p->width * (unsigned long long)(subset ? p->sample_count : p->spp);
             stats->segments = seg;
             // brute force: every Scene.Hit tests every sphere; BVH: exact tests counted by the kernel
             stats->sphere_tests = bvh_tests ? bvh_tests : seg * (unsigned long long)ctx->devs[0].n;
@@ -778,6 +802,43 @@ int tray_read_hdr(tray_ctx* ctx, double* hdr_out) {
             for (size_t r = 0; r < nrows; r++)
                 memcpy(hdr_out + (size_t)d.local_rows[r] * row_d, tmp.data() + r * row_d, row_d * sizeof(double));
         }
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
+int tray_device_sums(tray_ctx* ctx, double** device_ptr, uint64_t* n_doubles) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!device_ptr || !n_doubles) return fail(ctx, TRAY_E_INVALID, "tray_device_sums: null argument");
+    if (!ctx->have_hdr || !ctx->hdr_is_sums) return fail(ctx, TRAY_E_INVALID, "tray_device_sums: the last render was not a TRAY_SUMS_* render");
+    if (ctx->devs.size() != 1) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_device_sums: single-device contexts only (one process per GPU)");
+    *device_ptr = ctx->devs[0].hdr;
+    *n_doubles = (uint64_t)ctx->devs[0].local_rows.size() * (uint64_t)ctx->width * 3u;
+    return TRAY_OK;
+}
+
+int tray_resolve_sums(tray_ctx* ctx, uint64_t n_samples, uint8_t* rgba_out, size_t stride) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->have_hdr || !ctx->hdr_is_sums) return fail(ctx, TRAY_E_INVALID, "tray_resolve_sums: the last render was not a TRAY_SUMS_* render");
+    if (rgba_out && stride < (size_t)ctx->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_resolve_sums: stride < 4*width");
+    if (n_samples == 0) n_samples = ctx->sums_samples;
+    if (n_samples == 0) return fail(ctx, TRAY_E_INVALID, "tray_resolve_sums: no samples");
+    try {
+        for (Device& d : ctx->devs) {
+            const unsigned long long n_pixels = (unsigned long long)d.local_rows.size() * ctx->width;
+            if (!n_pixels) continue;
+            CK(cudaSetDevice(d.dev));
+            CombineArgs C;
+            C.partial[0] = d.hdr; C.n_parts = 1; C.n_pixels = n_pixels;
+            C.inv_spp = 1.0 / (double)n_samples;  // colorSumDiv, ray/tracer.go:123
+            C.rgba = d.rgba; C.hdr = nullptr; C.srgb_thr = d.srgb_thr;
+            combine_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, d.stream>>>(C);
+            CK(cudaGetLastError());
+        }
+        for (Device& d : ctx->devs) { CK(cudaSetDevice(d.dev)); CK(cudaStreamSynchronize(d.stream)); }
+        ctx->have_image = true;
+        if (rgba_out) copy_out(ctx, rgba_out, stride);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
 }

@@ -443,7 +443,7 @@ struct ResolveArgs {
     unsigned long long pass_pixel0;   // first local pixel
     int spp_local;
     double inv_spp;                   // 1.0 / float64(NumRaysPerPixel), ray/tracer.go:123
-    int partial;                      // 1: store the raw partial sum only (sample-split)
+    int partial;                      // 1: store the raw partial sum only (sample split / subsets); 2: continue the stored sum
     unsigned char* rgba;              // local image, 4 B/pixel
     double* hdr;                      // local, 3 doubles/pixel (mean, or partial sum when partial)
     const double* srgb_thr;
@@ -453,13 +453,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs R) {
     unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= R.n_pixels) return;
     const double* s = R.scratch + 3ull * p * (unsigned)R.spp_local;
+    unsigned long long lp = R.pass_pixel0 + p;
     double sx = 0.0, sy = 0.0, sz = 0.0;
+    if (R.partial == 2) { sx = R.hdr[3 * lp]; sy = R.hdr[3 * lp + 1]; sz = R.hdr[3 * lp + 2]; }  // progressive: same running sum
     for (int j = 0; j < R.spp_local; j++) {  // colorSum = Add(colorSum, color), sample order
         sx = sx + s[3 * j];
         sy = sy + s[3 * j + 1];
         sz = sz + s[3 * j + 2];
     }
-    unsigned long long lp = R.pass_pixel0 + p;
     if (R.partial) {
         R.hdr[3 * lp] = sx; R.hdr[3 * lp + 1] = sy; R.hdr[3 * lp + 2] = sz;
         return;

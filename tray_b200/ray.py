@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import rand  # noqa: F401  (fortio.org/rand host side: rand.New / rand.NewIdx)
+from ._lib import SUMS_ACCUMULATE, SUMS_OFF, SUMS_OVERWRITE  # noqa: F401
 from ._lib import ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, FP32, FP64_FMA, FP64_STRICT, FP64_STRICT_BRUTE, SPLIT_SAMPLES, SPLIT_TILES, STREAM_PER_SAMPLE, STREAM_REFERENCE, TrayError  # noqa: F401
 
 # ------------------------------------------------------------------------------------------------
@@ -264,6 +265,18 @@ class Context:
         _lib.check(self.handle, self._L.tray_read_hdr(self.handle, hdr.ctypes.data_as(C.c_void_p)))
         return hdr
 
+    def device_sums(self):
+        """(device pointer, number of doubles) of the raw colour sums left by the last SUMS_* render."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        _lib.check(self.handle, self._L.tray_device_sums(self.handle, C.byref(ptr), C.byref(n)))
+        return ptr.value, int(n.value)
+
+    def resolve_sums(self, n_samples=0, out=None):
+        ptr, stride = (None, 0)
+        if out is not None:
+            ptr, stride = out.ctypes.data_as(C.c_void_p), out.strides[0]
+        _lib.check(self.handle, self._L.tray_resolve_sums(self.handle, n_samples, ptr, stride))
+
     def first_hit(self, cam_c, width, height, precision=FP64_STRICT):
         ids = np.zeros((height, width), dtype=np.int32)
         t = np.zeros((height, width))
@@ -427,6 +440,35 @@ class Tracer(Camera):
         scene = self._prepare(scene)
         self._run(scene, self._params(0, self.height))
         return self.imageData
+
+    def RenderProgressive(self, scene, slice_rays):
+        """Additive (not in the reference, whose README lists navigation as WIP): the same frame as Render, delivered as
+        a sequence of refinements. Yields (rays_done, imageData) after every `slice_rays` rays per pixel; the scene and
+        the partial sums stay on the device, each slice continues the per-pixel sum in sample order, so the last image
+        is bit-identical to Render's."""
+        scene = self._prepare(scene)
+        ctx = self.Context or default_context()
+        ctx.upload(scene.flatten())
+        cam_c = self.to_c()
+        n, done = self.NumRaysPerPixel, 0
+        seed = self.Seed or (secrets.randbits(64) | 1)
+        stats = None
+        while done < n:
+            k = min(int(slice_rays), n - done)
+            p = self._params(0, self.height)
+            p.seed = seed
+            p.sample_offset, p.sample_stride, p.sample_count = done, 1, k
+            p.sums_mode = SUMS_OVERWRITE if done == 0 else SUMS_ACCUMULATE
+            st = ctx.render(cam_c, p, None)
+            if stats is None:
+                stats = dict(st)
+            else:
+                for key in ("paths", "segments", "sphere_tests", "depth_exhausted", "kernel_ms", "total_ms", "launches", "trace_kernel_ms"):
+                    stats[key] += st[key]
+            done += k
+            ctx.resolve_sums(done, self.imageData)
+            self.Stats = stats
+            yield done, self.imageData
 
     def RenderLines(self, idx, yStart, yEnd, scene):
         """(*Tracer).RenderLines (ray/tracer.go:120-155): rows [yStart,yEnd) only; idx = stream index
