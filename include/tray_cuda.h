@@ -16,6 +16,7 @@
  *   tray_camera        <- Camera after Initialize  ray/camera.go:9-39,43-105 (Initialize stays on the host)
  *   tray_first_hit     <- Scene.Hit + Sphere.Hit   ray/objects.go:37-46,81-104 (parity probe, RNG-free)
  *   tray_resolve_sums  <- the tail of RenderLines   ray/tracer.go:145-152 (colorSum * 1/N, ToSRGBA, Pix store)
+ *   tray_encode_png    <- SaveImage / png.Encode    main.go:26-36, benchmark/benchmark.go:23-33
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
  *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
  */
@@ -174,6 +175,15 @@ TRAY_API int tray_resolve_sums(tray_ctx *ctx, uint64_t n_samples, uint8_t *rgba_
  * rgba_small_out (cols*rows2*4) and ansi_out may each be NULL. ansi_len receives (rows2/2)*(cols*41+5). */
 TRAY_API int tray_present(tray_ctx *ctx, int32_t cols, int32_t rows2, uint8_t *rgba_small_out, uint8_t *ansi_out, size_t ansi_cap,
                           size_t *ansi_len, double *device_ms);
+
+/* The -save path (SaveImage -> png.Encode, main.go:26-36, benchmark/benchmark.go:23-33) on the device: encodes the last
+ * rendered frame (complete, resident on one device) as an 8-bit truecolour PNG -- what Go writes for an opaque
+ * *image.RGBA -- and copies the FILE bytes to png_out. Per-row adaptive filter, dynamic-Huffman deflate blocks, Adler-32
+ * and CRC-32 all run on the GPU; decoding the file returns exactly the rendered pixels (format parity = decoded pixels,
+ * not file bytes). png_len always receives the file size; png_out may be NULL (size query after encoding) and must hold
+ * png_len bytes otherwise (tray_png_bound gives a safe capacity up front). */
+TRAY_API size_t tray_png_bound(int32_t width, int32_t height);
+TRAY_API int tray_encode_png(tray_ctx *ctx, uint8_t *png_out, size_t cap, size_t *png_len, double *device_ms);
 
 /* RNG-independent parity probe: closest hit of every pixel-centre pinhole primary ray.
  * id -1 / t +Inf on a miss. Arrays are width*height (normal: x3). */

@@ -17,7 +17,7 @@ SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
-           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums")
+           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png")
 
 
 class TrayError(RuntimeError):
@@ -61,7 +61,7 @@ def library_path():
 
 def build_library(force=False, verbose=False):
     """Compile libtraycuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "zig_tables.h")]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "zig_tables.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "tray_cuda.h"))
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
@@ -102,6 +102,9 @@ def lib():
                                    C.POINTER(C.c_double)]
         L.tray_device_sums.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.tray_resolve_sums.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]
+        L.tray_png_bound.argtypes = [C.c_int32, C.c_int32]
+        L.tray_png_bound.restype = C.c_size_t
+        L.tray_encode_png.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
         L.tray_progress.argtypes = [C.c_void_p]
         L.tray_progress.restype = C.c_uint64
         L.tray_measure_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

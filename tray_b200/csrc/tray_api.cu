@@ -15,6 +15,7 @@
 
 #include "../../include/tray_cuda.h"
 #include "tray_kernels.cuh"
+#include "tray_png.cuh"
 
 using namespace tray;
 
@@ -942,6 +943,90 @@ int tray_present(tray_ctx* ctx, int32_t cols, int32_t rows2, uint8_t* rgba_small
         cudaFree(tmp); cudaFree(small); cudaFree(ansi);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
+}
+
+static uint32_t host_crc32(const uint8_t* p, size_t n) {
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    }
+    return ~c;
+}
+
+size_t tray_png_bound(int32_t width, int32_t height) {
+    if (width <= 0 || height <= 0) return 0;
+    const size_t raw = (size_t)height * (1 + 3 * (size_t)width);
+    return 2 * raw + 1024 * 1024;  // 15-bit codes at worst (< 2x), block headers, file framing
+}
+
+int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len, double* device_ms) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->have_image) return fail(ctx, TRAY_E_INVALID, "tray_encode_png: nothing rendered");
+    Device& d = ctx->devs[0];
+    if (ctx->y0 != 0 || ctx->y1 != ctx->height || (int)d.local_rows.size() != ctx->height)
+        return fail(ctx, TRAY_E_UNSUPPORTED, "tray_encode_png: needs a complete frame resident on one device (single-device context or sample split)");
+    if (!png_len) return fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_len is NULL");
+    try {
+        CK(cudaSetDevice(d.dev));
+        PngPlan P;
+        P.width = ctx->width; P.height = ctx->height; P.row_len = 1 + 3 * ctx->width;
+        // deflate blocks: >= 32 KB of scanlines each, about one block per SM when the image is large enough
+        int rpb = std::max((32768 + P.row_len - 1) / P.row_len, P.height / std::max(1, d.num_sms));
+        P.rows_per_block = std::max(1, rpb);
+        P.n_blocks = (P.height + P.rows_per_block - 1) / P.rows_per_block;
+        const size_t raw = (size_t)P.height * P.row_len;
+        const size_t out_cap = (tray_png_bound(P.width, P.height) + 15) / 16 * 16;
+        const size_t cap_pieces = out_cap / kCrcChunk + 2;
+        unsigned char *filt = nullptr, *out = nullptr;
+        unsigned *hist = nullptr, *piece = nullptr;
+        unsigned long long* row_adler = nullptr;
+        PngBlock* blocks = nullptr;
+        PngTotals* tot = nullptr;
+        CK(cudaMalloc(&filt, raw)); CK(cudaMalloc(&out, out_cap));
+        CK(cudaMalloc(&hist, sizeof(unsigned) * 256 * P.n_blocks)); CK(cudaMalloc(&piece, sizeof(unsigned) * cap_pieces));
+        CK(cudaMalloc(&row_adler, sizeof(unsigned long long) * 2 * P.height));
+        CK(cudaMalloc(&blocks, sizeof(PngBlock) * P.n_blocks)); CK(cudaMalloc(&tot, sizeof(PngTotals)));
+        // the fixed 43 bytes in front of the deflate stream: signature, IHDR chunk, IDAT length (patched on the device), "IDAT", zlib header
+        uint8_t pre[43] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n', 0, 0, 0, 13, 'I', 'H', 'D', 'R'};
+        auto be32 = [](uint8_t* q, uint32_t v) { q[0] = v >> 24; q[1] = v >> 16; q[2] = v >> 8; q[3] = v; };
+        be32(pre + 16, (uint32_t)P.width); be32(pre + 20, (uint32_t)P.height);
+        pre[24] = 8; pre[25] = 2; pre[26] = 0; pre[27] = 0; pre[28] = 0;  // 8 bit, truecolour, deflate, adaptive filtering, no interlace
+        be32(pre + 29, host_crc32(pre + 12, 17));
+        be32(pre + 33, 0);
+        memcpy(pre + 37, "IDAT", 4);
+        pre[41] = 0x78; pre[42] = 0x01;
+        cudaEvent_t a = next_event(d), b = next_event(d);
+        CK(cudaEventRecord(a, d.stream));
+        CK(cudaMemsetAsync(out, 0, out_cap, d.stream));
+        CK(cudaMemsetAsync(hist, 0, sizeof(unsigned) * 256 * P.n_blocks, d.stream));
+        CK(cudaMemcpyAsync(out, pre, sizeof pre, cudaMemcpyHostToDevice, d.stream));
+        png_filter_kernel<<<P.height, 256, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), P, filt, hist, row_adler);
+        png_huffman_kernel<<<P.n_blocks, 320, 0, d.stream>>>(hist, P, blocks);
+        png_layout_kernel<<<1, 32, 0, d.stream>>>(P, blocks, row_adler, tot);
+        png_pack_kernel<<<P.n_blocks, kPackThreads, 0, d.stream>>>(filt, P, blocks, reinterpret_cast<unsigned*>(out));
+        png_finish_kernel<<<1, 256, 0, d.stream>>>(out, tot, piece, 0);
+        png_crc_kernel<<<(unsigned)((cap_pieces + 255) / 256), 256, 0, d.stream>>>(out, tot, piece, cap_pieces);
+        png_finish_kernel<<<1, 256, 0, d.stream>>>(out, tot, piece, 1);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b, d.stream));
+        PngTotals ht;
+        CK(cudaMemcpyAsync(&ht, tot, sizeof ht, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (device_ms) *device_ms = ms;
+        *png_len = (size_t)ht.file_bytes;
+        int rc = TRAY_OK;
+        if (ht.file_bytes > out_cap) rc = fail(ctx, TRAY_E_CUDA, "tray_encode_png: internal bound exceeded");
+        else if (png_out) {
+            if (cap < ht.file_bytes) rc = fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_out too small (png_len holds the size needed)");
+            else CK(cudaMemcpy(png_out, out, (size_t)ht.file_bytes, cudaMemcpyDeviceToHost));
+        }
+        cudaFree(filt); cudaFree(out); cudaFree(hist); cudaFree(piece); cudaFree(row_adler); cudaFree(blocks); cudaFree(tot);
+        return rc;
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
 }
 
 uint64_t tray_progress(tray_ctx* ctx) {

@@ -313,6 +313,14 @@ class Context:
                                                      buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(ms)))
         return buf[:n.value].tobytes(), small, ms.value
 
+    def encode_png(self, width, height):
+        """SaveImage's png.Encode (main.go:26-36) on the device: returns (PNG file bytes, device ms)."""
+        cap = int(self._L.tray_png_bound(width, height))
+        buf = np.empty(cap, dtype=np.uint8)
+        n, ms = C.c_size_t(), C.c_double()
+        _lib.check(self.handle, self._L.tray_encode_png(self.handle, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(ms)))
+        return buf[:n.value].tobytes(), ms.value
+
     def progress(self):
         return int(self._L.tray_progress(self.handle))
 
@@ -478,6 +486,16 @@ class Tracer(Camera):
         p = self._params(yStart, yEnd, stream_idx=idx)
         p.num_workers = 0
         self._run(scene, p)
+
+
+def SaveImage(tracer, fname):
+    """main.go:26-36 / benchmark/benchmark.go:23-33 (SaveImage(img, fname) -> png.Encode): writes the tracer's last frame
+    as PNG. The file is encoded on the device from the frame still resident in HBM; returns the encode time in ms."""
+    ctx = tracer.Context or default_context()
+    data, ms = ctx.encode_png(tracer.width, tracer.height)
+    with open(fname, "wb") as f:
+        f.write(data)
+    return ms
 
 
 def New(width, height):
