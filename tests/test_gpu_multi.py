@@ -54,3 +54,19 @@ def test_sample_split_matches_within_rounding(ctx, g):
     d = np.abs(img.astype(int) - one.astype(int)).max(axis=2)
     assert (d <= 1).all() and (d == 0).mean() > 0.999
     multi.close()
+
+
+def test_png_of_a_tile_split_frame_gathers_on_device_zero(ctx):
+    """-save with the frame spread over devices: row bands are gathered onto device 0 by peer copies, then encoded there."""
+    import io
+    from PIL import Image
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene = ray.RichScene(rand.New(2))
+    w, h, spp, depth = 320, 181, 4, 20
+    multi = ray.Context([0, 1])
+    t = _tracer(multi, w, h, spp, depth)
+    img = t.Render(scene).copy()
+    data, _ = multi.encode_png(w, h)
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")), img[:, :, :3])
+    multi.close()

@@ -397,9 +397,7 @@ def test_present_downscale_and_ansi(ctx, O, w, h, cols, rows2):
 
 # ---- the C++ host layer: tray_b200/benchmark keeps the reference CLI (benchmark/benchmark.go:37-47) ----------------
 def test_cpp_benchmark_cli_matches_python_host(ctx, tmp_path):
-    import struct
     import subprocess
-    import zlib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "tray_b200", "benchmark")
     assert os.path.exists(exe), "run __graft_entry__.build()"
@@ -408,21 +406,9 @@ def test_cpp_benchmark_cli_matches_python_host(ctx, tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert "485 objects" in r.stderr  # the reference logs the object count (benchmark.go:68-69)
-    data = open(out, "rb").read()
-    assert data[:8] == b"\x89PNG\r\n\x1a\n"
-    pos, idat, dims = 8, b"", None
-    while pos < len(data):
-        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
-        body = data[pos + 8:pos + 8 + n]
-        if typ == b"IHDR":
-            dims = struct.unpack(">IIBBBBB", body)
-        if typ == b"IDAT":
-            idat += body
-        pos += 12 + n
-    assert dims[:4] == (96, 54, 8, 2)  # 8-bit RGB like the reference's opaque image.RGBA
-    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(54, 1 + 96 * 3)
-    assert (raw[:, 0] == 0).all()
-    rgb = raw[:, 1:].reshape(54, 96, 3)
+    from test_gpu_png import parse_png
+    rgb, chunks, _, _ = parse_png(open(out, "rb").read())  # 8-bit RGB like the reference's opaque image.RGBA; encoded on the GPU
+    assert chunks == [b"IHDR", b"IDAT", b"IEND"] and "PNG encoded on the GPU" in r.stderr
     t = tracer(96, 54, 4, 20)
     img = t.Render(ray.RichScene(rand.New(2)))
     assert np.array_equal(rgb, img[:, :, :3])

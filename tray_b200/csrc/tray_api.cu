@@ -965,11 +965,30 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!ctx->have_image) return fail(ctx, TRAY_E_INVALID, "tray_encode_png: nothing rendered");
     Device& d = ctx->devs[0];
-    if (ctx->y0 != 0 || ctx->y1 != ctx->height || (int)d.local_rows.size() != ctx->height)
-        return fail(ctx, TRAY_E_UNSUPPORTED, "tray_encode_png: needs a complete frame resident on one device (single-device context or sample split)");
+    size_t have_rows = 0;
+    for (Device& dv : ctx->devs) have_rows += dv.local_rows.size();
+    if (ctx->y0 != 0 || ctx->y1 != ctx->height || (int)have_rows != ctx->height)
+        return fail(ctx, TRAY_E_UNSUPPORTED, "tray_encode_png: needs a complete frame in this context (all rows, no external shards)");
     if (!png_len) return fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_len is NULL");
     try {
         CK(cudaSetDevice(d.dev));
+        // tile mode on several devices: gather the row bands onto device 0 (peer copies over NVLink), still no host pixels
+        const uchar4* frame = reinterpret_cast<const uchar4*>(d.rgba);
+        unsigned char* gathered = nullptr;
+        if ((int)d.local_rows.size() != ctx->height) {
+            const size_t row_bytes = (size_t)ctx->width * 4;
+            CK(cudaMalloc(&gathered, row_bytes * ctx->height));
+            for (Device& dv : ctx->devs) {
+                size_t r = 0, nrows = dv.local_rows.size();
+                while (r < nrows) {
+                    size_t e = r + 1;
+                    while (e < nrows && dv.local_rows[e] == dv.local_rows[e - 1] + 1) e++;
+                    CK(cudaMemcpyPeerAsync(gathered + (size_t)dv.local_rows[r] * row_bytes, d.dev, dv.rgba + r * row_bytes, dv.dev, (e - r) * row_bytes, d.stream));
+                    r = e;
+                }
+            }
+            frame = reinterpret_cast<const uchar4*>(gathered);
+        }
         PngPlan P;
         P.width = ctx->width; P.height = ctx->height; P.row_len = 1 + 3 * ctx->width;
         // deflate blocks: >= 32 KB of scanlines each, about one block per SM when the image is large enough
@@ -1002,7 +1021,7 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
         CK(cudaMemsetAsync(out, 0, out_cap, d.stream));
         CK(cudaMemsetAsync(hist, 0, sizeof(unsigned) * 256 * P.n_blocks, d.stream));
         CK(cudaMemcpyAsync(out, pre, sizeof pre, cudaMemcpyHostToDevice, d.stream));
-        png_filter_kernel<<<P.height, 256, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), P, filt, hist, row_adler);
+        png_filter_kernel<<<P.height, 256, 0, d.stream>>>(frame, P, filt, hist, row_adler);
         png_huffman_kernel<<<P.n_blocks, 320, 0, d.stream>>>(hist, P, blocks);
         png_layout_kernel<<<1, 32, 0, d.stream>>>(P, blocks, row_adler, tot);
         png_pack_kernel<<<P.n_blocks, kPackThreads, 0, d.stream>>>(filt, P, blocks, reinterpret_cast<unsigned*>(out));
@@ -1024,7 +1043,7 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
             if (cap < ht.file_bytes) rc = fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_out too small (png_len holds the size needed)");
             else CK(cudaMemcpy(png_out, out, (size_t)ht.file_bytes, cudaMemcpyDeviceToHost));
         }
-        cudaFree(filt); cudaFree(out); cudaFree(hist); cudaFree(piece); cudaFree(row_adler); cudaFree(blocks); cudaFree(tot);
+        cudaFree(gathered); cudaFree(filt); cudaFree(out); cudaFree(hist); cudaFree(piece); cudaFree(row_adler); cudaFree(blocks); cudaFree(tot);
         return rc;
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
 }

@@ -1,51 +1,12 @@
 // benchmark.cpp -- the reference's batch driver (benchmark/benchmark.go:35-101) on the CUDA backend: same flags
 // (-r -d -w -seed -width -height -save), RichScene(rand.New(seed)), RichSceneCamera, Render, PNG save.
 // Extra flags: -gpus N (devices 0..N-1), -fma (fused discriminant), -ref (reference chunk streams, honours -w).
-#include <zlib.h>
-
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "tray.hpp"
-
-static void be32(std::vector<uint8_t>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s)); }
-static void chunk(FILE* f, const char* type, const std::vector<uint8_t>& data) {
-    std::vector<uint8_t> b;
-    be32(b, (uint32_t)data.size());
-    b.insert(b.end(), type, type + 4);
-    b.insert(b.end(), data.begin(), data.end());
-    uint32_t crc = crc32(0, b.data() + 4, (uInt)(b.size() - 4));
-    be32(b, crc);
-    fwrite(b.data(), 1, b.size(), f);
-}
-// image/png writes an opaque *image.RGBA as 8-bit RGB (colour type 2, like example.png)
-static bool SaveImage(const ray::RGBA& img, const std::string& fname) {
-    FILE* f = fopen(fname.c_str(), "wb");
-    if (!f) return false;
-    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    fwrite(sig, 1, 8, f);
-    std::vector<uint8_t> ihdr;
-    be32(ihdr, (uint32_t)img.W); be32(ihdr, (uint32_t)img.H);
-    ihdr.insert(ihdr.end(), {8, 2, 0, 0, 0});
-    chunk(f, "IHDR", ihdr);
-    std::vector<uint8_t> raw((size_t)img.H * (1 + 3 * (size_t)img.W));
-    for (int y = 0; y < img.H; y++) {
-        uint8_t* o = raw.data() + (size_t)y * (1 + 3 * img.W);
-        *o++ = 0;
-        const uint8_t* s = img.Pix.data() + (size_t)y * img.Stride;
-        for (int x = 0; x < img.W; x++) { *o++ = s[4 * x]; *o++ = s[4 * x + 1]; *o++ = s[4 * x + 2]; }
-    }
-    uLongf zl = compressBound((uLong)raw.size());
-    std::vector<uint8_t> z(zl);
-    if (compress2(z.data(), &zl, raw.data(), (uLong)raw.size(), 6) != Z_OK) { fclose(f); return false; }
-    z.resize(zl);
-    chunk(f, "IDAT", z);
-    chunk(f, "IEND", {});
-    fclose(f);
-    return true;
-}
 
 int main(int argc, char** argv) {
     int rays = 10, depth = 20, workers = 1, width = 1200, height = 675, gpus = 1;  // benchmark.go:37-46 defaults
@@ -86,13 +47,13 @@ int main(int argc, char** argv) {
         rt->StreamMode = ref ? TRAY_STREAM_REFERENCE : TRAY_STREAM_PER_SAMPLE;
         for (int g = 0; g < gpus; g++) rt->Devices.push_back(g);
         auto t0 = std::chrono::steady_clock::now();
-        ray::RGBA& img = rt->Render(&scene);
+        rt->Render(&scene);
         double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "Rendered in %.3f s (kernels %.1f ms): %.1f Mpaths/s, %.1f Mrays/s on %d GPU(s)\n", s, rt->Stats.kernel_ms,
                 rt->Stats.paths / rt->Stats.kernel_ms / 1e3, rt->Stats.segments / rt->Stats.kernel_ms / 1e3, rt->Stats.n_devices);
         if (!save.empty()) {
-            if (!SaveImage(img, save)) { fprintf(stderr, "could not save image to \"%s\"\n", save.c_str()); return 1; }
-            fprintf(stderr, "Saved rendered image to \"%s\"\n", save.c_str());
+            double ms = rt->SaveImage(save);  // PNG encoded on the device (tray_encode_png)
+            fprintf(stderr, "Saved rendered image to \"%s\" (PNG encoded on the GPU in %.2f ms)\n", save.c_str(), ms);
         }
     } catch (const std::exception& e) {
         fprintf(stderr, "%s\n", e.what());

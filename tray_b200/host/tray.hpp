@@ -6,6 +6,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <memory>
 #include <random>
 #include <stdexcept>
@@ -188,6 +189,21 @@ class Tracer : public Camera {  // ray/tracer.go:25-35
     void RenderLines(int idx, int yStart, int yEnd, Scene& scene) { run(scene, yStart, yEnd, idx, 0); }
     RGBA& Image() { return imageData_; }
     uint64_t Progress() const { return ctx_ ? tray_progress(ctx_) : 0; }
+    // SaveImage(img, fname) (main.go:26-36, benchmark/benchmark.go:23-33): the PNG file of the last frame, encoded on the
+    // device from the frame still resident in HBM. Returns the device time of the encode in ms.
+    double SaveImage(const std::string& fname) {
+        if (!ctx_) throw std::runtime_error("SaveImage: nothing rendered");
+        std::vector<uint8_t> png(tray_png_bound(width_, height_));
+        size_t n = 0;
+        double ms = 0;
+        check(tray_encode_png(ctx_, png.data(), png.size(), &n, &ms));
+        FILE* f = fopen(fname.c_str(), "wb");
+        if (!f) throw std::runtime_error("could not create " + fname);
+        bool ok = fwrite(png.data(), 1, n, f) == n;
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw std::runtime_error("could not write " + fname);
+        return ms;
+    }
 
    private:
     void check(int rc) {
