@@ -170,7 +170,7 @@ TRAY_API int tray_resolve_sums(tray_ctx *ctx, uint64_t n_samples, uint8_t *rgba_
 
 /* The interactive path after Render (main.go:119-130), on the device: scale the last rendered frame (which must be
  * complete and resident on one device) to cols x rows2 pixels with draw.BiLinear semantics (x/image/draw, draw.Over onto
- * a fresh image), then emit the half-block truecolor frame for a cols x rows2/2 terminal: per cell the fixed-width
+ * a fresh image) -- or draw.NearestNeighbor when the frame is narrower than cols (tray -s < 1) --, then emit the half-block truecolor frame for a cols x rows2/2 terminal: per cell the fixed-width
  * record ESC[48;2;RRR;GGG;BBBm ESC[38;2;RRR;GGG;BBBm U+2584 (41 bytes), per row ESC[0m LF (5 bytes).
  * rgba_small_out (cols*rows2*4) and ansi_out may each be NULL. ansi_len receives (rows2/2)*(cols*41+5). */
 TRAY_API int tray_present(tray_ctx *ctx, int32_t cols, int32_t rows2, uint8_t *rgba_small_out, uint8_t *ansi_out, size_t ansi_cap,

@@ -299,6 +299,17 @@ def bilinear_scale(src, dw, dh):
     return dst
 
 
+def nn_scale(src, dw, dh):
+    """draw.NearestNeighbor.Scale(..., draw.Over, nil) onto a fresh RGBA (main.go:124-125, tray -s < 1)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    sh, sw = src.shape[:2]
+    dst = np.zeros((dh, dw, 4), dtype=np.uint8)
+    lib().oracle_nn_scale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    if lib().oracle_nn_scale(_p(src), sw, sh, src.strides[0], dw, dh, _p(dst)) != 0:
+        raise RuntimeError("oracle_nn_scale failed")
+    return dst
+
+
 def ansi_halfblocks(img):
     """Half-block truecolor frame of an (2*rows, cols, 4) image (fixed-width records, see tray_oracle.c)."""
     img = np.ascontiguousarray(img, dtype=np.uint8)

@@ -866,6 +866,25 @@ static uint16_t bl_ftou(double f) {
     return 0;
 }
 
+/* draw.NearestNeighbor.Scale(dst, dst.Bounds(), src, src.Bounds(), draw.Over, nil) onto a fresh RGBA (main.go:124-125;
+ * golang.org/x/image/draw nnInterpolator, restated: third-party, parity unpinned): integer source coordinates
+ * sx = (2*dx+1)*sw/(2*dw), sy likewise; 16-bit premultiplied Over onto a zeroed destination. */
+EXPORT int oracle_nn_scale(const uint8_t *src, int sw, int sh, size_t sstride, int dw, int dh, uint8_t *dst /* dw*dh*4, zeroed */) {
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return -1;
+    uint64_t dw2 = 2 * (uint64_t)dw, dh2 = 2 * (uint64_t)dh;
+    for (int dy = 0; dy < dh; dy++) {
+        uint64_t sy = (2 * (uint64_t)dy + 1) * (uint64_t)sh / dh2;
+        for (int dx = 0; dx < dw; dx++) {
+            uint64_t sx = (2 * (uint64_t)dx + 1) * (uint64_t)sw / dw2;
+            const uint8_t *px = src + (size_t)sy * sstride + 4 * (size_t)sx;
+            uint32_t pa = (uint32_t)px[3] * 0x101, a1 = (0xffff - pa) * 0x101;
+            uint8_t *d = dst + 4 * ((size_t)dy * dw + dx);
+            for (int k = 0; k < 4; k++) d[k] = (uint8_t)(((uint32_t)d[k] * a1 / 0xffff + (uint32_t)px[k] * 0x101) >> 8);
+        }
+    }
+    return 0;
+}
+
 EXPORT int oracle_bilinear_scale(const uint8_t *src, int sw, int sh, size_t sstride, int dw, int dh, uint8_t *dst /* dw*dh*4, zeroed */) {
     if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return -1;
     double *tmp = (double *)malloc(sizeof(double) * 4 * (size_t)dw * (size_t)sh);

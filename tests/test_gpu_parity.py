@@ -395,6 +395,17 @@ def test_present_downscale_and_ansi(ctx, O, w, h, cols, rows2):
     assert (cells[..., 38:] == np.array([0xE2, 0x96, 0x84], dtype=np.uint8)).all()
 
 
+@pytest.mark.parametrize("w,h,cols,rows2", [(80, 45, 160, 90), (53, 31, 160, 90), (159, 90, 160, 90)])
+def test_present_nearest_neighbor_upscale(ctx, O, w, h, cols, rows2):
+    """tray -s < 1 (main.go:124-125): the frame is smaller than the terminal and is scaled up with draw.NearestNeighbor."""
+    t = tracer(w, h, 2, 12)
+    img = t.Render(ray.RichScene(rand.New(2))).copy()
+    ansi, small, _ = ctx.present(cols, rows2)
+    want = O.nn_scale(img, cols, rows2)
+    assert np.array_equal(small, want) and ansi == O.ansi_halfblocks(want)
+    assert {tuple(p) for p in small.reshape(-1, 4)} <= {tuple(p) for p in img.reshape(-1, 4)}  # only source pixels
+
+
 # ---- the C++ host layer: tray_b200/benchmark keeps the reference CLI (benchmark/benchmark.go:37-47) ----------------
 def test_cpp_benchmark_cli_matches_python_host(ctx, tmp_path):
     import subprocess

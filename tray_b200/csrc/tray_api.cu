@@ -929,8 +929,12 @@ int tray_present(tray_ctx* ctx, int32_t cols, int32_t rows2, uint8_t* rgba_small
         CK(cudaMalloc(&ansi, need));
         cudaEvent_t a = next_event(d), b = next_event(d);
         CK(cudaEventRecord(a, d.stream));
-        scale_x_kernel<<<dim3((cols + 127) / 128, sh), 128, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), sw, sh, cols, tmp);
-        scale_y_kernel<<<dim3((cols + 127) / 128, rows2), 128, 0, d.stream>>>(tmp, cols, sh, rows2, small);
+        if (sw < cols) {  // supersample < 1: the frame is smaller than the terminal -> draw.NearestNeighbor (main.go:124-125)
+            scale_nn_kernel<<<dim3((cols + 127) / 128, rows2), 128, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), sw, sh, cols, rows2, small);
+        } else {          // draw.BiLinear (main.go:126-127); identity when the sizes agree (supersample == 1: no scaling at all)
+            scale_x_kernel<<<dim3((cols + 127) / 128, sh), 128, 0, d.stream>>>(reinterpret_cast<const uchar4*>(d.rgba), sw, sh, cols, tmp);
+            scale_y_kernel<<<dim3((cols + 127) / 128, rows2), 128, 0, d.stream>>>(tmp, cols, sh, rows2, small);
+        }
         ansi_kernel<<<dim3((cols + 1 + 127) / 128, rows2 / 2), 128, 0, d.stream>>>(small, cols, rows2 / 2, ansi);
         CK(cudaGetLastError());
         CK(cudaEventRecord(b, d.stream));

@@ -711,6 +711,17 @@ __global__ void __launch_bounds__(128) scale_y_kernel(const double4* __restrict_
     dst[(size_t)y * dw + x] = make_uchar4((unsigned char)(q0 >> 8), (unsigned char)(q1 >> 8), (unsigned char)(q2 >> 8), (unsigned char)(q3 >> 8));
 }
 
+// draw.NearestNeighbor.Scale with draw.Over onto a fresh image (tray -s < 1, main.go:124-125): x/image/draw samples the source
+// pixel ((2*dx+1)*sw/(2*dw), (2*dy+1)*sh/(2*dh)) in integer arithmetic; the 16-bit premultiplied Over of an opaque
+// pixel onto zero gives (v*0x101) >> 8 = v, for a translucent one (v*0x101) >> 8 too (destination contributes 0).
+__global__ void __launch_bounds__(128) scale_nn_kernel(const uchar4* __restrict__ src, int sw, int sh, int dw, int dh, uchar4* __restrict__ dst) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    unsigned long long sx = (2ull * (unsigned)x + 1ull) * (unsigned)sw / (2ull * (unsigned)dw);
+    unsigned long long sy = (2ull * (unsigned)y + 1ull) * (unsigned)sh / (2ull * (unsigned)dh);
+    dst[(size_t)y * dw + x] = src[(size_t)sy * sw + sx];
+}
+
 constexpr int kAnsiCell = 41, kAnsiEol = 5;
 // One thread per terminal cell: ESC[48;2;RRR;GGG;BBBm ESC[38;2;RRR;GGG;BBBm U+2584 ; thread x == w writes ESC[0m LF.
 __global__ void __launch_bounds__(128) ansi_kernel(const uchar4* __restrict__ img, int w, int rows, unsigned char* __restrict__ out) {
