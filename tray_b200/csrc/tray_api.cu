@@ -461,27 +461,28 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
                 pr[i] = make_double4(0, 0, 0, 0);
             }
         }
-        // fp32 pre-filter table: pairs of spheres, two float4 each. Spheres whose magnitudes would blow up the
-        // filter's error bound (|c|_inf > 256 or r*r > 256, e.g. the r=1000 ground sphere) are stored as NaN:
-        // never "certainly missed", i.e. always exact-tested. Padding: r2 = -inf (always missed).
+        // fp32 pre-filter table: pairs of spheres, two float4 each: (Cx0,Cx1,Cy0,Cy1), (Cz0,Cz1,-K0,-K1) with K = |C|^2 - r^2
+        // (fp64 on the host, then rounded). Spheres whose magnitudes would blow up the filter's error bound
+        // (|c|_inf > 256 or r*r > 256, e.g. the r=1000 ground sphere) are stored as NaN: never "certainly missed", i.e.
+        // always exact-tested. Padding: -K = -inf (always missed).
         std::vector<float4> fp((size_t)n_pad);
         float mc = 0.f, r2max = 0.f;
         const float qnan = std::numeric_limits<float>::quiet_NaN(), finf = std::numeric_limits<float>::infinity();
         for (int j = 0; j < n_pad / 2; j++) {
-            float c[2][3], nr2[2];
+            float c[2][3], nk[2];
             for (int k = 0; k < 2; k++) {
                 int i = 2 * j + k;
-                if (i >= n) { c[k][0] = c[k][1] = c[k][2] = 0.f; nr2[k] = finf; continue; }  // -r2 = +inf
+                if (i >= n) { c[k][0] = c[k][1] = c[k][2] = 0.f; nk[k] = -finf; continue; }
                 double cm = std::max(std::fabs(sc->cx[i]), std::max(std::fabs(sc->cy[i]), std::fabs(sc->cz[i])));
                 double r2 = sc->radius[i] * sc->radius[i];
-                if (!(cm <= 256.0) || !(r2 <= 256.0)) { c[k][0] = c[k][1] = c[k][2] = qnan; nr2[k] = qnan; continue; }
+                if (!(cm <= 256.0) || !(r2 <= 256.0)) { c[k][0] = c[k][1] = c[k][2] = qnan; nk[k] = qnan; continue; }
                 c[k][0] = (float)sc->cx[i]; c[k][1] = (float)sc->cy[i]; c[k][2] = (float)sc->cz[i];
-                nr2[k] = -(float)r2;
+                nk[k] = -(float)((sc->cx[i] * sc->cx[i] + sc->cy[i] * sc->cy[i] + sc->cz[i] * sc->cz[i]) - r2);
                 mc = std::max(mc, (float)cm * 1.0000002f);
                 r2max = std::max(r2max, (float)r2 * 1.0000002f);
             }
             fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
-            fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nr2[0], nr2[1]);
+            fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nk[0], nk[1]);
         }
         HostBvh hb = bvh_build(sc);
         for (Device& d : ctx->devs) {

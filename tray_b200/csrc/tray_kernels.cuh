@@ -271,45 +271,47 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
             if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
         } else if constexpr (GEO == kGeoFilter) {
-            // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction) ----
-            // A test is skipped only when the fp32 evaluation PROVES the strict fp64 test returns false
-            // ("exact pre-filter"): with T = K1*L + K2 bounding every fp32/conversion error,
-            //   val1 = h^2 - a*(C - T) < 0            =>  disc < 0 in exact and in fp64 arithmetic
-            //   h + sqrt(a)*T < 0  and  C - T >= 0    =>  h < 0 <= c                  (both roots <= 0)
-            // Everything else (incl. NaN entries = spheres outside the filter's range) goes to the exact path.
+            // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction, 8 instructions per pair) ----
+            // A test is skipped only when the fp32 evaluation PROVES that Sphere.Hit returns false in strict fp64
+            // ("exact pre-filter"). Per sphere, with d = D/|D|, h~ = d.(C-O), c = |C-O|^2 - r^2 and the
+            // table holding (C, -(|C|^2 - r^2)):
+            //   hp ~ h~ + EH = d.C - d.O + EH        (3 FMA)      |hp - (h~ + EH)| <= Eh = 16u R < EH,   R = max|C|inf + |O|inf
+            //   nc ~ -c + E                          (1 ADD + 3 FMA, expanded as -(|C|^2 - r^2) - |O|^2 + 2 O.C + E)
+            //   v1 = hp*hp + nc                      (1 FMA)      errors of nc and of this rounding <= u (22 R^2 + 6.2 max r^2) < E
+            //   v1 < 0 :  h~ >= 0  =>  hp >= h~ >= 0, so h~^2 - c <= hp^2 - c < 0: disc < 0 in exact and in fp64 arithmetic
+            //             h~ <  0  =>  c > hp^2 + (E - error) > 0: h < 0 < c, both roots <= 0 (or disc < 0)
+            //   hp < 0 and nc < 0  =>  h~ < 0 < c as well
+            // Everything else (incl. NaN table entries = spheres outside the filter's range, canonical NaN has sign 0)
+            // goes to the exact path.
             const float u32 = 5.9604645e-8f;
-            const float fox = (float)(double)ox, foy = (float)(double)oy, foz = (float)(double)oz;
-            const float fdx = (float)(double)dx, fdy = (float)(double)dy, fdz = (float)(double)dz;
-            const float fa = (float)(double)a;
-            const float mo = fmaxf(fabsf(fox), fmaxf(fabsf(foy), fabsf(foz)));
-            const float eps = 5.3f * u32 * (S.filt_mc + mo);          // >= sqrt(3)*3u*(|c|+|o|): |oc_f - oc|_2
-            float k1 = 1.01f * (64.0f * u32 + 3.0f * eps);
-            float k2 = 1.01f * (3.0f * eps + 6.0f * eps * eps + 16.0f * u32 * S.filt_r2max + 8.0f * u32 + 1e-30f);
-            if (!(eps < 0.25f)) k2 = __int_as_float(0x7f800000);      // origin too far out: filter off for this ray
-            const float2 nO_x = make_float2(-fox, -fox), nO_y = make_float2(-foy, -foy), nO_z = make_float2(-foz, -foz);
+            const double inv_n = 1.0 / sqrt((double)a);
+            const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
+            const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+            float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+            const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+            const float R = S.filt_mc + mo;
+            float eh = 17.5f * u32 * R;                                             // > 1.01 * Eh
+            float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+                                 ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));  // E - |O|^2
+            if (!(mo < 1e6f)) { noot = __int_as_float(0x7f800000); eh = 0.0f; }     // origin too far out: filter off for this ray
+            ndo += eh;                                                              // one more rounding <= u(|d.O| + EH), inside Eh
             const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
-            const float2 nA = make_float2(-fa, -fa);
-            const float saf = 1.001f * sqrtf(fa);
-            const float2 SA = make_float2(saf, saf), K1 = make_float2(k1, k1), K2 = make_float2(k2, k2);
-            const float2 nK2 = make_float2(-k2, -k2), OMK1 = make_float2(1.0f - k1, 1.0f - k1);
+            const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
+            const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
+            const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
 #pragma unroll 1
             for (int i = 0; i < n_pad; i += CH) {
                 unsigned mask = 0;
 #pragma unroll
                 for (int u = 0; u < CH / 2; u++) {
                     const float4 g0 = sfp[i + 2 * u], g1 = sfp[i + 2 * u + 1];
-                    float2 ocx = __fadd2_rn(make_float2(g0.x, g0.y), nO_x);
-                    float2 ocy = __fadd2_rn(make_float2(g0.z, g0.w), nO_y);
-                    float2 ocz = __fadd2_rn(make_float2(g1.x, g1.y), nO_z);
-                    float2 h = __ffma2_rn(Dz, ocz, __ffma2_rn(Dy, ocy, __fmul2_rn(Dx, ocx)));
-                    float2 L = __ffma2_rn(ocz, ocz, __ffma2_rn(ocy, ocy, __fmul2_rn(ocx, ocx)));
-                    float2 nr2k = __fadd2_rn(make_float2(g1.z, g1.w), nK2);   // -(r2 + K2)
-                    float2 cm = __ffma2_rn(L, OMK1, nr2k);                     // C - T
-                    float2 t = __ffma2_rn(K1, L, K2);                          // T
-                    float2 v1 = __ffma2_rn(h, h, __fmul2_rn(nA, cm));          // h^2 - a*(C - T)
-                    float2 v2 = __ffma2_rn(SA, t, h);                          // h + sqrt(a)*T
-                    int mx = __float_as_int(v1.x) | (__float_as_int(v2.x) & ~__float_as_int(cm.x));
-                    int my = __float_as_int(v1.y) | (__float_as_int(v2.y) & ~__float_as_int(cm.y));
+                    const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
+                    float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
+                    float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);                    // -(|C|^2 - r^2) - |O|^2 + E
+                    float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
+                    float2 v1 = __ffma2_rn(h, h, nc);
+                    int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
+                    int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
                     mask = __funnelshift_l((unsigned)mx, mask, 1);
                     mask = __funnelshift_l((unsigned)my, mask, 1);
                 }
