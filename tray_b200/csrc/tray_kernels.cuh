@@ -299,23 +299,37 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
             const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
             const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
+            // Software-pipelined by half chunks: while the two pairs in registers A are evaluated, the LDS.128 of the next
+            // two pairs (B) are in flight, and vice versa; the table is followed by other shared data, so the last prefetch
+            // reads valid (unused) memory. One running shared-memory address, immediate offsets.
+            static_assert(CH == 8, "the pre-filter loop is written for chunks of 8 spheres");
+            auto lds4 = [](float4& v, unsigned addr) {
+                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            };
+            unsigned mask = 0;
+            auto pair = [&](const float4& g0, const float4& g1) {
+                const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
+                float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
+                float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);                    // -(|C|^2 - r^2) - |O|^2 + E
+                float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
+                float2 v1 = __ffma2_rn(h, h, nc);
+                int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
+                int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
+                mask = __funnelshift_l((unsigned)mx, mask, 1);
+                mask = __funnelshift_l((unsigned)my, mask, 1);
+            };
+            unsigned saddr = (unsigned)__cvta_generic_to_shared(sfp);
+            float4 a0, a1, a2, a3, b0, b1, b2, b3;
+            lds4(a0, saddr); lds4(a1, saddr + 16); lds4(a2, saddr + 32); lds4(a3, saddr + 48);
 #pragma unroll 1
             for (int i = 0; i < n_pad; i += CH) {
-                unsigned mask = 0;
-#pragma unroll
-                for (int u = 0; u < CH / 2; u++) {
-                    const float4 g0 = sfp[i + 2 * u], g1 = sfp[i + 2 * u + 1];
-                    const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
-                    float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
-                    float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);                    // -(|C|^2 - r^2) - |O|^2 + E
-                    float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
-                    float2 v1 = __ffma2_rn(h, h, nc);
-                    int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
-                    int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
-                    mask = __funnelshift_l((unsigned)mx, mask, 1);
-                    mask = __funnelshift_l((unsigned)my, mask, 1);
-                }
-                mask = has ? (~mask & ((1u << CH) - 1u)) : 0u;  // 1 = must be tested exactly (idle lanes: nothing)
+                lds4(b0, saddr + 64); lds4(b1, saddr + 80); lds4(b2, saddr + 96); lds4(b3, saddr + 112);
+                mask = 0;
+                pair(a0, a1); pair(a2, a3);
+                lds4(a0, saddr + 128); lds4(a1, saddr + 144); lds4(a2, saddr + 160); lds4(a3, saddr + 176);
+                pair(b0, b1); pair(b2, b3);
+                saddr += 128;
+                mask = ~mask & 0xffu;  // 1 = must be tested exactly
                 if (mask_prev) {
                     if (ncand > kCand - CH) {  // list about to overflow (rare): run the exact test on what is queued
                         push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                         m &= ~(1u << bit);
                     } while (m);
                 }
-                mask_prev = mask;
+                mask_prev = has ? mask : 0u;  // idle lanes queue nothing
             }
         } else {
         // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
