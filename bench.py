@@ -211,6 +211,7 @@ def run_ours(args):
     tr = ray.New(w, h)
     tr.Camera = ray.RichSceneCamera()
     tr.MaxDepth, tr.NumRaysPerPixel, tr.Seed, tr.Precision = depth, spp, SEED, precision
+    tr.Layout = {"auto": ray.LAYOUT_AUTO, "plain": ray.LAYOUT_PLAIN, "regroup": ray.LAYOUT_REGROUP}[args.layout]
     split_samples = args.split == "samples" and world > 1
     tr.ShardIndex, tr.ShardCount = (rank, world) if (world > 1 and not split_samples) else (0, 0)
     tr.Context = ctx
@@ -337,6 +338,23 @@ def run_ours(args):
             alts.append({"precision": name, "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
                          "roofline": {"bound": "fp64", "achieved": a_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": a_tf / peak_tf},
                          "note": notes[name]})
+        # same default arithmetic, other divergence layout / closest-hit structure (results bit-identical)
+        for name, setp, note in (
+                ("fp64, plain layout", lambda q: setattr(q, "layout", ray.LAYOUT_PLAIN),
+                 "default kernel without the per-material regrouping of paths inside the CTA (TRAY_LAYOUT_PLAIN)"),
+                ("fp64, bvh", lambda q: setattr(q, "accel", ray.ACCEL_BVH),
+                 "small BVH instead of the linear scan (TRAY_ACCEL_BVH): far fewer sphere tests, so no roofline claim; image bit-identical")):
+            p2 = tr._params(0, h)
+            setp(p2)
+            for _ in range(2):
+                ctx.render(cam_c, p2, None)
+            a_ms, a_paths, a_tests, a_seg = 0.0, 0, 0, 0
+            for _ in range(args.steps):
+                st2 = ctx.render(cam_c, p2, None)
+                a_ms += st2["kernel_ms"]; a_paths += st2["paths"]; a_tests += st2["sphere_tests"]; a_seg += st2["segments"]
+            a_ms = max_over_ranks(a_ms)
+            alts.append({"precision": name, "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+                         "sphere_tests_per_segment": a_tests / max(1, a_seg), "note": note})
         # fp32 fast path: throughput + PSNR of its 8-bit image against the fp64 image (same streams)
         if world == 1:
             p3 = tr._params(0, h)
@@ -390,6 +408,28 @@ def run_ours(args):
     my_rows = st["paths"] // (w * spp)
     d2h = int(ansi_bytes) if interactive else (int(h * w * 4) if split_samples else int(my_rows * w * 4))
 
+    # ---- the -save path: PNG of the frame encoded on the device (outside every timed region above) ----
+    save_png = None
+    if world == 1 and not interactive and not args.no_alt:
+        import io
+        ctx.render(cam_c, params, None)
+        t0 = time.perf_counter()
+        png, png_ms = ctx.encode_png(w, h)
+        png_wall = (time.perf_counter() - t0) * 1e3
+        save_png = {"bytes": len(png), "device_ms": png_ms, "wall_ms_incl_d2h": png_wall, "raw_rgb_bytes": w * h * 3,
+                    "note": "tray_encode_png: adaptive filter + dynamic-Huffman deflate + Adler-32/CRC-32 on the GPU; only the file crosses PCIe"}
+        try:
+            from PIL import Image
+            t0 = time.perf_counter()
+            buf = io.BytesIO()
+            Image.fromarray(host_img[:, :, :3]).save(buf, format="PNG")
+            save_png["cpu_pillow_ms"] = (time.perf_counter() - t0) * 1e3
+            save_png["cpu_pillow_bytes"] = buf.tell()
+            save_png["decoded_equal"] = bool(np.array_equal(np.asarray(Image.open(io.BytesIO(png)).convert("RGB")), host_img[:, :, :3]))
+        except Exception as e:  # Pillow missing: the device numbers stand alone
+            save_png["cpu_pillow_ms"] = None
+            save_png["cpu_note"] = str(e)
+
     # ---- CPU baseline + parity spot check (rank 0, N=1 only) ----
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -413,7 +453,7 @@ def run_ours(args):
             "mrays_per_s": all_segments / (dev_ms * 1e-3) / 1e6,
             "wall_ms_per_step": wall_ms / args.steps,
             "config": {"workload": workload, "desc": desc, "width": w, "height": h, "rays_per_pixel": spp, "max_depth": depth,
-                       "seed": SEED, "spheres": n_spheres, "precision": args.precision, "streams": "per-sample",
+                       "seed": SEED, "spheres": n_spheres, "precision": args.precision, "streams": "per-sample", "layout": args.layout,
                        "parallelism": ("samples%d+nccl_reduce" if split_samples else "tiles%d") % world if world > 1 else "1gpu",
                        "l2": "256 MiB memset between timed steps (L2 flush); working set is 31 kB of spheres in shared memory"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
@@ -433,12 +473,12 @@ def run_ours(args):
                          "peak_dadd_dmul_tflops": peak_strict_tf, "peak_ffma_tflops": peak_f32_tf,
                          "loop_only_probe_tflops": loop_probe_tf,
                          "structural_ceiling_frac": {"fp64": 18.0 / 34.0, "fp64-brute": 18.0 / 34.0, "fp64-fma": 18.0 / 22.0, "fp32": 18.0 / 22.0}[args.precision],
-                         "pipe_analysis": ({"bound": "fp32", "pipe_slot_tflops": segments * float(-(-n_spheres // 8) * 8) * 30.0 / (trace_ms * 1e-3) / 1e12,
+                         "pipe_analysis": ({"bound": "fp32", "pipe_slot_tflops": segments * float(-(-n_spheres // 8) * 8) * 16.0 / (trace_ms * 1e-3) / 1e12,
                                             "peak_ffma2_tflops": peak_ffma2_tf,
-                                            "frac": segments * float(-(-n_spheres // 8) * 8) * 30.0 / (trace_ms * 1e-3) / 1e12 / peak_ffma2_tf,
-                                            "note": "the default kernel proves ~99 % of the tests missed with 15 packed fp32 instructions per PAIR of spheres "
-                                                    "(FFMA2 = 4 pipe-slot flops), so the fp64-roofline fraction above can exceed the 0.529 ceiling of the pure "
-                                                    "FP64-pipe kernel (alt_modes: fp64-brute); results are bit-identical"}
+                                            "frac": segments * float(-(-n_spheres // 8) * 8) * 16.0 / (trace_ms * 1e-3) / 1e12 / peak_ffma2_tf,
+                                            "note": "the default kernel proves ~99 % of the tests missed with 8 packed fp32 instructions per PAIR of spheres "
+                                                    "(FFMA2 = 4 pipe-slot flops -> 16 per sphere), so the fp64-roofline fraction above can exceed the 0.529 "
+                                                    "ceiling of the pure FP64-pipe kernel (alt_modes: fp64-brute); results are bit-identical"}
                                            if args.precision == "fp64" and not uses_bvh else None),
                          "note": "achieved = algorithmic flops (SURVEY 8d: 18 per sphere test) / CUDA-event time of the trace kernel; compute-bound, HBM traffic "
                                  "is ~30 B/path of scratch; tensor cores do not apply"},
@@ -454,6 +494,8 @@ def run_ours(args):
                                            "frame, only the ANSI bytes cross PCIe"}
         if alts:
             line["alt_modes"] = alts
+        if save_png:
+            line["save_png"] = save_png
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if parity:
@@ -482,6 +524,8 @@ def main():
                          "fp64-fma = fused discriminant; fp32 = fast path")
     ap.add_argument("--split", default="tiles", choices=["tiles", "samples"],
                     help="N>1 partitioning: interleaved row bands (no collective, default) or sample split + NCCL sum-reduce")
+    ap.add_argument("--layout", default="auto", choices=["auto", "plain", "regroup"],
+                    help="divergence layout of the trace kernel (results identical): plain megakernel or per-material regrouping")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -70,6 +70,13 @@ extern "C" {
 #define TRAY_ACCEL_BRUTE 1 /* linear scan of the sphere table (the reference's Scene.Hit order) */
 #define TRAY_ACCEL_BVH 2   /* small BVH (median split, <= 4 spheres per leaf) built on the host at upload */
 
+/* divergence layout of the trace kernel. Results are identical for all of them. */
+#define TRAY_LAYOUT_AUTO 0
+#define TRAY_LAYOUT_PLAIN 1   /* megakernel, a path stays in its lane from generation to termination */
+#define TRAY_LAYOUT_REGROUP 2 /* megakernel with per-material regrouping: after Scene.Hit the paths of a CTA are sorted through
+                                 shared memory by what happens next (miss | Lambertian | Metal | Dielectric), so scatter,
+                                 generators, unwind and regeneration run on mostly homogeneous warps */
+
 /* multi-GPU partitioning inside one context */
 #define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */
 #define TRAY_SPLIT_SAMPLES 1 /* each GPU renders samples s == g (mod G); partial sums reduced over NVLink */
@@ -125,6 +132,8 @@ typedef struct {
      * the sum in sample order, so the image after the last slice is bit-identical to the one-shot render. */
     int32_t sample_offset, sample_stride, sample_count;
     int32_t sums_mode;    /* TRAY_SUMS_* */
+    int32_t layout;       /* TRAY_LAYOUT_*: how the megakernel deals with divergence (0 = automatic) */
+    int32_t reserved[3];
 } tray_params;
 
 typedef struct {

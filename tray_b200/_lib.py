@@ -14,6 +14,7 @@ FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
 SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
+LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP = 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
@@ -42,7 +43,7 @@ class Params(C.Structure):
                 ("stream_mode", C.c_int32), ("num_workers", C.c_int32), ("stream_idx", C.c_int64),
                 ("precision", C.c_int32), ("split_mode", C.c_int32), ("shard_index", C.c_int32),
                 ("shard_count", C.c_int32), ("accel", C.c_int32), ("sample_offset", C.c_int32), ("sample_stride", C.c_int32),
-                ("sample_count", C.c_int32), ("sums_mode", C.c_int32)]
+                ("sample_count", C.c_int32), ("sums_mode", C.c_int32), ("layout", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):

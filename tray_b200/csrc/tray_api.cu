@@ -108,6 +108,7 @@ struct Device {
     uint8_t* rgba = nullptr; size_t rgba_cap = 0;       // bytes
     double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
     unsigned long long* counters = nullptr; int counters_cap = 0;
+    unsigned short* stk_g = nullptr; size_t stk_cap = 0;  // regroup layout: attenuation stacks [level][slot]
     unsigned long long* stats = nullptr;     // [0] segments [1] depth exhausted [2] progress samples
     double* srgb_thr = nullptr;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
@@ -212,11 +213,36 @@ constexpr int kTPB = TRAY_TPB;        // threads per CTA of the trace kernel
 constexpr int kMinBlocks = TRAY_MINB; // resident CTAs per SM the register allocation targets
 constexpr size_t kSmemBudget = 200 * 1024;
 
+// Regroup layout (pre-filter kernel only): same launch shape, plus the exchange area in shared memory and the
+// attenuation stacks in global memory (max_depth x lanes x 2 bytes, L2 resident).
+template <typename T, bool FMA>
+void launch_trace_regroup(Device& d, TraceArgs A, const DevScene<T>& S, size_t smem) {
+#ifndef TRAY_FILTER_MINB
+#define TRAY_FILTER_MINB 4
+#endif
+    auto k = trace_kernel<T, FMA, kTPB, TRAY_FILTER_MINB, kGeoFilter, true>;
+    smem = ((smem + 15) & ~(size_t)15) + sizeof(RegroupBuf<kTPB>);
+    int bps = 0;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
+    if (bps < 1) bps = 1;
+    const unsigned grid = (unsigned)(d.num_sms * bps);
+    A.n_slots = grid * kTPB;
+    grow(d.stk_g, d.stk_cap, (size_t)A.n_slots * (size_t)A.max_depth);
+    A.stk_g = d.stk_g;
+    GeoArg<T, kGeoFilter> none{};
+    k<<<grid, kTPB, smem, d.stream>>>(A, S, none);
+    CK(cudaGetLastError());
+}
+
 template <typename T, bool FMA, int GEO>
 void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S, const GeoArg<T, GEO>& GP, size_t smem) {
     // register budget: the pre-filter kernel keeps both the fp32 filter state and the fp64 ray live: 128 regs x 16 warps/SM
     // measured best (140.8 vs 143.3 ms); the pure-fp64 kernels prefer 96 regs x 20 warps/SM (211.8 vs 216.7 ms).
-    constexpr int minb = (GEO == kGeoFilter && kMinBlocks > 4) ? 4 : kMinBlocks;
+#ifndef TRAY_FILTER_MINB
+#define TRAY_FILTER_MINB 4
+#endif
+    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : kMinBlocks;
     auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -228,7 +254,7 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 
 template <typename T, bool FMA>
 struct TraceLaunch {
-    static void run(const Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, bool bvh = false) {
+    static void run(Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, bool bvh = false, bool regroup = false) {
         typedef typename Vec4T<T>::type T4;
         const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
         const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
@@ -239,6 +265,7 @@ struct TraceLaunch {
                 return;
             }
             if (filter && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
+                if (regroup) { launch_trace_regroup<T, FMA>(d, A, S, (size_t)S.n_pad * 16 + tail); return; }
                 GeoArg<T, kGeoFilter> none{};
                 launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
                 return;
@@ -260,10 +287,14 @@ struct TraceLaunch {
     }
 };
 
-void launch_trace(const tray_ctx* ctx, const Device& d, const TraceArgs& A, int precision, int accel) {
+#ifndef TRAY_DEFAULT_LAYOUT
+#define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_REGROUP  // measured: 103.1 ms vs 107.9 ms plain on config 2 (profiles/r01_*)
+#endif
+void launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precision, int accel, int layout) {
     const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
+    const bool regroup = (layout == TRAY_LAYOUT_AUTO ? TRAY_DEFAULT_LAYOUT : layout) == TRAY_LAYOUT_REGROUP;
     if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
-    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh);
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh, regroup);
     else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
 }
@@ -420,7 +451,7 @@ void tray_destroy(tray_ctx* ctx) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         free_scene(d);
-        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stats); cudaFree(d.srgb_thr);
+        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g); cudaFree(d.stats); cudaFree(d.srgb_thr);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         for (cudaEvent_t e : d.ev_pool) cudaEventDestroy(e);
@@ -567,6 +598,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
     if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP64_STRICT_BRUTE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
     if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_BVH) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
+    if (p->layout < TRAY_LAYOUT_AUTO || p->layout > TRAY_LAYOUT_REGROUP) return fail(ctx, TRAY_E_INVALID, "tray_render: bad layout");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
     if (p->sums_mode < TRAY_SUMS_OFF || p->sums_mode > TRAY_SUMS_ACCUMULATE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad sums_mode");
@@ -691,8 +723,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.band_rows = kBandRows; A.shard_count = shard_count; A.shard_index = shard_index;
                     A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
+                    A.stk_g = nullptr; A.n_slots = 0;
                     CK(cudaEventRecord(next_event(d), d.stream));
-                    launch_trace(ctx, d, A, p->precision, p->accel);
+                    launch_trace(ctx, d, A, p->precision, p->accel, p->layout);
                     CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;

@@ -37,6 +37,8 @@ struct TraceArgs {
     double* scratch;                 // n_samples x 3 linear colours, [pixel][sample][rgb]
     unsigned long long* stats;       // [0] segments  [1] depth exhausted
     unsigned long long* progress;    // samples finished (for tray_progress), may be null
+    unsigned short* stk_g;           // regroup layout: attenuation stacks, [level][slot] (slot = launch-wide lane id)
+    unsigned n_slots;
 };
 
 __device__ __forceinline__ int map_row(const TraceArgs& A, int ly) {
@@ -182,7 +184,21 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
     }
 }
 
-template <typename T, bool FMA, int TPB, int MINB, int GEO>
+// Exchange area of the regroup layout (one per CTA, shared memory): the path state of every lane, SoA.
+template <int TPB>
+struct RegroupBuf {
+    double f[7][TPB];               // O, D, best_t
+    unsigned long long r[2][TPB];   // generator state
+    int i[5][TPB];                  // depth_left, sp, sample index, best (-1: miss, -2: no path), stack slot
+    int count[5][TPB / 32];         // lanes per (class, warp)
+};
+
+// REGROUP (layout "per-material queues inside the megakernel"): after Scene.Hit the TPB paths of the CTA are sorted by what
+// happens next -- miss (sky, finish, regenerate) | Lambertian | Metal | Dielectric | no path -- through shared memory, so
+// that the divergent tail of the iteration (scatter, generators, unwind, regeneration) runs on warps that are mostly of
+// one kind. Paths have no lane affinity; the attenuation stack lives in global memory under a slot id that travels with
+// the path. Results are bit-identical to the plain layout (pure data movement).
+template <typename T, bool FMA, int TPB, int MINB, int GEO, bool REGROUP = false>
 __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
                                                           const __grid_constant__ GeoArg<T, GEO> GP) {
     typedef typename Vec4T<T>::type T4;
@@ -193,6 +209,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     float4* sfp = reinterpret_cast<float4*>(smem_raw);  // kGeoFilter: n_pad/2 pairs x 2 float4
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
+    RegroupBuf<TPB>* xb = reinterpret_cast<RegroupBuf<TPB>*>(smem_raw + ((geo_bytes + sizeof(ZigTables) + (size_t)kCand * TPB * sizeof(uint16_t) + 15) & ~(size_t)15));
     const int tid = threadIdx.x;
     if (GEO == kGeoShared)
         for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
@@ -213,7 +230,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     V3<T> O = mk<T>(T(0), T(1e18), T(0)), D = mk<T>(T(0), T(1), T(0));
     Pcg rng = pcg_new_idx(0, 0);
     int depth_left = 0, sp = 0;
-    uint16_t stk[kMaxDepth];
+    uint16_t stk[REGROUP ? 1 : kMaxDepth];
+    unsigned slot = blockIdx.x * TPB + tid;  // regroup layout: where this path's attenuation stack lives
     unsigned long long nseg = 0, ntests = 0;
     unsigned nexh = 0, ndone = 0, ntests_blk = 0;
     const int n_pad = S.n_pad;
@@ -259,13 +277,18 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                 need = __ballot_sync(kFull, !has);
             }
         }
-        if (!__any_sync(kFull, has)) break;
+        const bool warp_alive = __any_sync(kFull, has);
+        if constexpr (!REGROUP) {
+            if (!warp_alive) break;
+        }  // regroup layout: the CTA leaves together, decided at the exchange barrier below
 
         // ---------------- Scene.Hit: brute force over all spheres ----------------
+        T best_t = t_inf<T>();
+        int best = -1;
+        if (warp_alive) {  // (regroup layout: warps left without a path near the end of a pass skip the scan)
         const T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
         const T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
-        T best_t = t_inf<T>();
-        int best = -1, ncand = 0;
+        int ncand = 0;
         unsigned mask_prev = 0;
         if constexpr (GEO == kGeoBVH) {
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
@@ -369,6 +392,50 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         if (mask_prev)
             push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
         resolve_candidates<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+        }
+
+        // ---------------- regroup: sort the CTA's paths by what happens next ----------------
+        if constexpr (REGROUP) {
+            const int warp = tid >> 5;
+            int cls = 4;  // no path
+            if (has) cls = best < 0 ? 0 : 1 + (int)S.kind[best];
+            unsigned bal[5];
+#pragma unroll
+            for (int c = 0; c < 5; c++) bal[c] = __ballot_sync(kFull, cls == c);
+            unsigned mine = bal[0];
+#pragma unroll
+            for (int c = 1; c < 5; c++) if (cls == c) mine = bal[c];
+            const int rank = __popc(mine & lt_mask);
+            if (lane < 5) {
+                unsigned v = bal[0];
+#pragma unroll
+                for (int c = 1; c < 5; c++) if (lane == c) v = bal[c];
+                xb->count[lane][warp] = __popc(v);
+            }
+            if (!__syncthreads_or(has ? 1 : 0)) break;  // no path left in the CTA (and none to be had: regeneration ran dry)
+            int dst = rank;
+#pragma unroll
+            for (int c = 0; c < 5; c++)
+#pragma unroll
+                for (int w = 0; w < TPB / 32; w++) {
+                    const int n = xb->count[c][w];
+                    if (c < cls || (c == cls && w < warp)) dst += n;
+                }
+            xb->f[0][dst] = (double)O.x; xb->f[1][dst] = (double)O.y; xb->f[2][dst] = (double)O.z;
+            xb->f[3][dst] = (double)D.x; xb->f[4][dst] = (double)D.y; xb->f[5][dst] = (double)D.z;
+            xb->f[6][dst] = (double)best_t;
+            xb->r[0][dst] = rng.hi; xb->r[1][dst] = rng.lo;
+            xb->i[0][dst] = depth_left; xb->i[1][dst] = sp; xb->i[2][dst] = (int)my_li;
+            xb->i[3][dst] = has ? best : -2; xb->i[4][dst] = (int)slot;
+            __syncthreads();
+            O = mk<T>(T(xb->f[0][tid]), T(xb->f[1][tid]), T(xb->f[2][tid]));
+            D = mk<T>(T(xb->f[3][tid]), T(xb->f[4][tid]), T(xb->f[5][tid]));
+            best_t = T(xb->f[6][tid]);
+            rng.hi = xb->r[0][tid]; rng.lo = xb->r[1][tid];
+            depth_left = xb->i[0][tid]; sp = xb->i[1][tid]; my_li = (unsigned)xb->i[2][tid];
+            best = xb->i[3][tid]; slot = (unsigned)xb->i[4][tid];
+            has = best != -2;
+        }
 
         // ---------------- RayColor step (ray/objects.go:49-62) ----------------
         if (has) {
@@ -414,7 +481,11 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                 if (!scattered) {
                     finish = true;  // absorbed: black
                 } else {
-                    if (kind != 2) stk[sp++] = (uint16_t)best;  // attenuation = albedo; Dielectric's (1,1,1) is an exact identity
+                    if (kind != 2) {  // attenuation = albedo; Dielectric's (1,1,1) is an exact identity
+                        if constexpr (REGROUP) A.stk_g[(size_t)sp * A.n_slots + slot] = (uint16_t)best;
+                        else stk[sp] = (uint16_t)best;
+                        sp++;
+                    }
                     O = P; D = D2;
                     depth_left--;
                     if (depth_left <= 0) { finish = true; nexh++; }  // RayColor(depth<=0) = black
@@ -423,7 +494,10 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             if (finish) {
                 if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
                     for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56
-                        double4 prm = S.params[stk[k]];
+                        int id;
+                        if constexpr (REGROUP) id = A.stk_g[(size_t)k * A.n_slots + slot];
+                        else id = stk[k];
+                        double4 prm = S.params[id];
                         col = vmul(mk<T>(T(prm.x), T(prm.y), T(prm.z)), col);
                     }
                 }

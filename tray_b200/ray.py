@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from . import rand  # noqa: F401  (fortio.org/rand host side: rand.New / rand.NewIdx)
-from ._lib import SUMS_ACCUMULATE, SUMS_OFF, SUMS_OVERWRITE  # noqa: F401
+from ._lib import LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, SUMS_ACCUMULATE, SUMS_OFF, SUMS_OVERWRITE  # noqa: F401
 from ._lib import ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, FP32, FP64_FMA, FP64_STRICT, FP64_STRICT_BRUTE, SPLIT_SAMPLES, SPLIT_TILES, STREAM_PER_SAMPLE, STREAM_REFERENCE, TrayError  # noqa: F401
 
 # ------------------------------------------------------------------------------------------------
@@ -363,6 +363,7 @@ class Tracer(Camera):
         self.Precision = FP64_STRICT  # exact Go/amd64 float64 semantics; FP64_FMA is the opt-in fused mode
         self.SplitMode = SPLIT_TILES
         self.Accel = ACCEL_AUTO
+        self.Layout = LAYOUT_AUTO
         self.ShardIndex, self.ShardCount = 0, 0
         self.Context = None
         self.Stats = None
@@ -409,7 +410,7 @@ class Tracer(Camera):
         p.seed = seed
         p.y0, p.y1 = y0, y1
         p.stream_mode, p.num_workers, p.stream_idx = self.StreamMode, self.NumWorkers, stream_idx
-        p.precision, p.split_mode, p.accel = self.Precision, self.SplitMode, self.Accel
+        p.precision, p.split_mode, p.accel, p.layout = self.Precision, self.SplitMode, self.Accel, self.Layout
         p.shard_index, p.shard_count = self.ShardIndex, self.ShardCount
         return p
 
