@@ -109,6 +109,14 @@ struct Device {
     double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
     unsigned long long* counters = nullptr; int counters_cap = 0;
     unsigned short* stk_g = nullptr; size_t stk_cap = 0;  // regroup layout: attenuation stacks [level][slot]
+    // PNG encoder work buffers (tray_encode_png), kept between calls
+    unsigned char* png_filt = nullptr; size_t png_filt_cap = 0;
+    unsigned char* png_out = nullptr; size_t png_out_cap = 0;
+    unsigned* png_hist = nullptr; size_t png_hist_cap = 0;
+    unsigned* png_piece = nullptr; size_t png_piece_cap = 0;
+    unsigned long long* png_adler = nullptr; size_t png_adler_cap = 0;
+    PngBlock* png_blocks = nullptr; size_t png_blocks_cap = 0;
+    PngTotals* png_tot = nullptr; size_t png_tot_cap = 0;
     unsigned long long* stats = nullptr;     // [0] segments [1] depth exhausted [2] progress samples
     double* srgb_thr = nullptr;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
@@ -451,7 +459,8 @@ void tray_destroy(tray_ctx* ctx) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         free_scene(d);
-        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g); cudaFree(d.stats); cudaFree(d.srgb_thr);
+        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g);
+        cudaFree(d.png_filt); cudaFree(d.png_out); cudaFree(d.png_hist); cudaFree(d.png_piece); cudaFree(d.png_adler); cudaFree(d.png_blocks); cudaFree(d.png_tot); cudaFree(d.stats); cudaFree(d.srgb_thr);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         for (cudaEvent_t e : d.ev_pool) cudaEventDestroy(e);
@@ -1036,15 +1045,15 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
         const size_t raw = (size_t)P.height * P.row_len;
         const size_t out_cap = (tray_png_bound(P.width, P.height) + 15) / 16 * 16;
         const size_t cap_pieces = out_cap / kCrcChunk + 2;
-        unsigned char *filt = nullptr, *out = nullptr;
-        unsigned *hist = nullptr, *piece = nullptr;
-        unsigned long long* row_adler = nullptr;
-        PngBlock* blocks = nullptr;
-        PngTotals* tot = nullptr;
-        CK(cudaMalloc(&filt, raw)); CK(cudaMalloc(&out, out_cap));
-        CK(cudaMalloc(&hist, sizeof(unsigned) * 256 * P.n_blocks)); CK(cudaMalloc(&piece, sizeof(unsigned) * cap_pieces));
-        CK(cudaMalloc(&row_adler, sizeof(unsigned long long) * 2 * P.height));
-        CK(cudaMalloc(&blocks, sizeof(PngBlock) * P.n_blocks)); CK(cudaMalloc(&tot, sizeof(PngTotals)));
+        grow(d.png_filt, d.png_filt_cap, raw); grow(d.png_out, d.png_out_cap, out_cap);
+        grow(d.png_hist, d.png_hist_cap, (size_t)256 * P.n_blocks); grow(d.png_piece, d.png_piece_cap, cap_pieces);
+        grow(d.png_adler, d.png_adler_cap, (size_t)2 * P.height);
+        grow(d.png_blocks, d.png_blocks_cap, (size_t)P.n_blocks); grow(d.png_tot, d.png_tot_cap, (size_t)1);
+        unsigned char *filt = d.png_filt, *out = d.png_out;
+        unsigned *hist = d.png_hist, *piece = d.png_piece;
+        unsigned long long* row_adler = d.png_adler;
+        PngBlock* blocks = d.png_blocks;
+        PngTotals* tot = d.png_tot;
         // the fixed 43 bytes in front of the deflate stream: signature, IHDR chunk, IDAT length (patched on the device), "IDAT", zlib header
         uint8_t pre[43] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n', 0, 0, 0, 13, 'I', 'H', 'D', 'R'};
         auto be32 = [](uint8_t* q, uint32_t v) { q[0] = v >> 24; q[1] = v >> 16; q[2] = v >> 8; q[3] = v; };
@@ -1081,7 +1090,7 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
             if (cap < ht.file_bytes) rc = fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_out too small (png_len holds the size needed)");
             else CK(cudaMemcpy(png_out, out, (size_t)ht.file_bytes, cudaMemcpyDeviceToHost));
         }
-        cudaFree(gathered); cudaFree(filt); cudaFree(out); cudaFree(hist); cudaFree(piece); cudaFree(row_adler); cudaFree(blocks); cudaFree(tot);
+        cudaFree(gathered);
         return rc;
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
 }
