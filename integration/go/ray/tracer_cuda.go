@@ -187,6 +187,13 @@ func (t *Tracer) renderCUDA(scene *Scene, y0, y1, idx int) error {
 	if CUDASampleSplit {
 		p.split_mode = C.TRAY_SPLIT_SAMPLES
 	}
+	if cudaSubset.mode != 0 { // RenderProgressive / multi-process sample split: raw colour sums stay on the device
+		p.sample_offset, p.sample_stride, p.sample_count = C.int32_t(cudaSubset.offset), C.int32_t(cudaSubset.stride), C.int32_t(cudaSubset.count)
+		p.sums_mode = cudaSubset.mode
+	}
+	if os.Getenv("TRAY_LAYOUT") == "plain" { // default: per-material regrouping inside the CTA (same results)
+		p.layout = C.TRAY_LAYOUT_PLAIN
+	}
 	// ProgressFunc: poll the library from a goroutine; deltas sum to the pixel count (tracer_test.go:172-186).
 	done := make(chan struct{})
 	var wg sync.WaitGroup
@@ -246,4 +253,91 @@ func (t *Tracer) RenderLines(idx, yStart, yEnd int, scene *Scene) {
 	if err := t.renderCUDA(scene, yStart, yEnd, idx); err != nil {
 		panic(err)
 	}
+}
+
+// ---- additive API over the rest of the C ABI (the callers either side of Render in main.go / benchmark.go) ----
+
+// EncodePNG returns the PNG file of the last rendered frame, encoded on the GPU from the frame still resident in
+// HBM (tray_encode_png). It replaces png.Encode inside SaveImage (main.go:26-36, benchmark/benchmark.go:23-33):
+//
+//	func SaveImage(rt *ray.Tracer, fname string) error { b, err := rt.EncodePNG(); if err != nil { return err }; return os.WriteFile(fname, b, 0o644) }
+//
+// Decoding the file gives back exactly img.Pix's R,G,B (8-bit truecolour, what image/png writes for an opaque RGBA).
+func (t *Tracer) EncodePNG() ([]byte, error) {
+	cuda.mu.Lock()
+	defer cuda.mu.Unlock()
+	ctx := cudaContext()
+	buf := make([]byte, int(C.tray_png_bound(C.int32_t(t.width), C.int32_t(t.height))))
+	var n C.size_t
+	if rc := C.tray_encode_png(ctx, (*C.uint8_t)(unsafe.Pointer(&buf[0])), C.size_t(len(buf)), &n, nil); rc != 0 {
+		return nil, fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+	}
+	return buf[:int(n)], nil
+}
+
+// Present is the tail of tray's OnResize (main.go:119-130) on the GPU: the last frame scaled to cols x 2*rows pixels
+// (draw.BiLinear, or draw.NearestNeighbor when the frame is smaller than the terminal: -s < 1) and emitted as the
+// half-block truecolor frame for a cols x rows terminal. Only the ANSI bytes cross PCIe; write them to the terminal
+// in place of ap.ShowScaledImage(resized).
+func (t *Tracer) Present(cols, rows int) ([]byte, error) {
+	cuda.mu.Lock()
+	defer cuda.mu.Unlock()
+	ctx := cudaContext()
+	out := make([]byte, rows*(cols*41+5))
+	var n C.size_t
+	rc := C.tray_present(ctx, C.int32_t(cols), C.int32_t(2*rows), nil, (*C.uint8_t)(unsafe.Pointer(&out[0])), C.size_t(len(out)), &n, nil)
+	if rc != 0 {
+		return nil, fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+	}
+	return out[:int(n)], nil
+}
+
+// RenderProgressive delivers the same frame as Render as a sequence of refinements (README "WIP: navigation in the
+// world"): after every `slice` rays per pixel, show(raysDone, img) is called with the mean over the rays so far. The
+// scene and the per-pixel colour sums stay on the device and each slice continues the sum in sample order
+// (tray_params.sums_mode), so the last image is bit-identical to Render's. show may return false to stop early
+// (a key was pressed: re-render from the new camera).
+func (t *Tracer) RenderProgressive(scene *Scene, slice int, show func(raysDone int, img *image.RGBA) bool) error {
+	scene = t.prepare(scene)
+	seed := t.Seed
+	if seed == 0 {
+		seed = randomSeed()
+	}
+	saved := t.Seed
+	t.Seed = seed
+	defer func() { t.Seed = saved }()
+	for done := 0; done < t.NumRaysPerPixel; {
+		k := min(slice, t.NumRaysPerPixel-done)
+		mode := C.int32_t(C.TRAY_SUMS_ACCUMULATE)
+		if done == 0 {
+			mode = C.TRAY_SUMS_OVERWRITE
+		}
+		if err := t.renderSubset(scene, done, 1, k, mode); err != nil { // renderCUDA with p.sample_* / p.sums_mode set
+			return err
+		}
+		done += k
+		ctx := cudaContext()
+		pix := t.imageData.Pix
+		if rc := C.tray_resolve_sums(ctx, C.uint64_t(done), (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.size_t(t.imageData.Stride)); rc != 0 {
+			return fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+		}
+		if show != nil && !show(done, t.imageData) {
+			return nil
+		}
+	}
+	return nil
+}
+
+// subset carries the sample-subset fields of tray_params for one renderCUDA call (zero = all samples, classic render).
+type subset struct {
+	offset, stride, count int
+	mode                  C.int32_t
+}
+
+var cudaSubset subset // read by renderCUDA when filling tray_params: p.sample_offset/stride/count, p.sums_mode
+
+func (t *Tracer) renderSubset(scene *Scene, offset, stride, count int, mode C.int32_t) error {
+	cudaSubset = subset{offset, stride, count, mode}
+	defer func() { cudaSubset = subset{} }()
+	return t.renderCUDA(scene, 0, t.height, -1)
 }

@@ -59,7 +59,12 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 tmp = os.path.join(G, "src.csv")
 open(tmp, "w").write(src)
 out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), tmp], capture_output=True, text=True).stdout
+src2 = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+tmp2 = os.path.join(G, "src_lines.csv")
+open(tmp2, "w").write(src2)
+lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), tmp2, "45"], capture_output=True, text=True).stdout
 open(os.path.join(P, tag + "_trace_kernel%s_source_summary.txt" % suffix), "w").write(
-    "ncu --set full --import-source on, source page of tray::trace_kernel (first profiled launch)\n\n" + out)
+    "ncu --set full --import-source on, source page of tray::trace_kernel (first profiled launch)\n\n" + out +
+    "\nby CUDA source line (stall samples, warp-instructions, active threads per instruction):\n" + lines)
 print(open(os.path.join(P, tag + "_launch_summary.txt")).read())
 print(out[:1500])
