@@ -531,9 +531,25 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    buf = io.StringIO()
+    sys.stdout = buf
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout = sys.__stdout__
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    out = buf.getvalue()
+    if out:
+        sys.stdout.write(out)
+        sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":
