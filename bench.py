@@ -211,7 +211,7 @@ def run_ours(args):
     tr = ray.New(w, h)
     tr.Camera = ray.RichSceneCamera()
     tr.MaxDepth, tr.NumRaysPerPixel, tr.Seed, tr.Precision = depth, spp, SEED, precision
-    tr.Layout = {"auto": ray.LAYOUT_AUTO, "plain": ray.LAYOUT_PLAIN, "regroup": ray.LAYOUT_REGROUP}[args.layout]
+    tr.Layout = {"auto": ray.LAYOUT_AUTO, "plain": ray.LAYOUT_PLAIN, "regroup": ray.LAYOUT_REGROUP, "wavefront": ray.LAYOUT_WAVEFRONT}[args.layout]
     split_samples = args.split == "samples" and world > 1
     tr.ShardIndex, tr.ShardCount = (rank, world) if (world > 1 and not split_samples) else (0, 0)
     tr.Context = ctx
@@ -525,7 +525,7 @@ def main():
                          "fp64-fma = fused discriminant; fp32 = fast path")
     ap.add_argument("--split", default="tiles", choices=["tiles", "samples"],
                     help="N>1 partitioning: interleaved row bands (no collective, default) or sample split + NCCL sum-reduce")
-    ap.add_argument("--layout", default="auto", choices=["auto", "plain", "regroup"],
+    ap.add_argument("--layout", default="auto", choices=["auto", "plain", "regroup", "wavefront"],
                     help="divergence layout of the trace kernel (results identical): plain megakernel or per-material regrouping")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -77,6 +77,9 @@ extern "C" {
                                  shared memory by what happens next (miss | Lambertian | Metal | Dielectric), so scatter,
                                  generators, unwind and regeneration run on mostly homogeneous warps */
 
+#define TRAY_LAYOUT_WAVEFRONT 3 /* path state in HBM, one bounce = intersect | shade (per-material queues) | regenerate kernels
+                                  (strict fp64 linear scan only; other modes fall back to the regroup megakernel) */
+
 /* multi-GPU partitioning inside one context */
 #define TRAY_SPLIT_TILES 0   /* interleaved row bands; device-to-host gather only */
 #define TRAY_SPLIT_SAMPLES 1 /* each GPU renders samples s == g (mod G); partial sums reduced over NVLink */

@@ -407,21 +407,23 @@ def test_present_nearest_neighbor_upscale(ctx, O, w, h, cols, rows2):
 
 
 @pytest.mark.parametrize("w,h,spp,depth", [(400, 225, 10, 50), (7, 5, 1, 3), (129, 63, 3, 50), (64, 36, 64, 200)])
-def test_regroup_layout_is_bit_identical(ctx, w, h, spp, depth):
-    """TRAY_LAYOUT_REGROUP only moves path state between lanes (per-material sorting through shared memory): images,
-    linear-HDR means and every counter must equal the plain megakernel's, bit for bit."""
+def test_layouts_are_bit_identical(ctx, w, h, spp, depth):
+    """TRAY_LAYOUT_REGROUP (per-material sorting of the CTA's paths through shared memory) and TRAY_LAYOUT_WAVEFRONT (path
+    state in HBM, per-material queues, one kernel per stage) only move path state around: images, linear-HDR means and
+    every counter must equal the plain megakernel's, bit for bit."""
     scene = ray.RichScene(rand.New(2))
     a = tracer(w, h, spp, depth)
     a.Layout = ray.LAYOUT_PLAIN
     ia = a.Render(scene).copy()
     ha = ctx.read_hdr(w, h)
-    b = tracer(w, h, spp, depth)
-    b.Layout = ray.LAYOUT_REGROUP
-    ib = b.Render(scene).copy()
-    hb = ctx.read_hdr(w, h)
-    assert np.array_equal(ia, ib) and np.array_equal(ha, hb)
-    for k in ("paths", "segments", "sphere_tests", "depth_exhausted"):
-        assert a.Stats[k] == b.Stats[k], k
+    for layout in (ray.LAYOUT_REGROUP, ray.LAYOUT_WAVEFRONT):
+        b = tracer(w, h, spp, depth)
+        b.Layout = layout
+        ib = b.Render(scene).copy()
+        hb = ctx.read_hdr(w, h)
+        assert np.array_equal(ia, ib) and np.array_equal(ha, hb), layout
+        for k in ("paths", "segments", "sphere_tests", "depth_exhausted"):
+            assert a.Stats[k] == b.Stats[k], (layout, k)
 
 
 # ---- the C++ host layer: tray_b200/benchmark keeps the reference CLI (benchmark/benchmark.go:37-47) ----------------

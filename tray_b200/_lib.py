@@ -14,7 +14,7 @@ FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
 SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
-LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP = 0, 1, 2
+LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, LAYOUT_WAVEFRONT = 0, 1, 2, 3
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
@@ -62,7 +62,7 @@ def library_path():
 
 def build_library(force=False, verbose=False):
     """Compile libtraycuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "zig_tables.h")]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "tray_wavefront.cuh", "zig_tables.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "tray_cuda.h"))
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:

@@ -16,6 +16,7 @@
 #include "../../include/tray_cuda.h"
 #include "tray_kernels.cuh"
 #include "tray_png.cuh"
+#include "tray_wavefront.cuh"
 
 using namespace tray;
 
@@ -109,6 +110,12 @@ struct Device {
     double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
     unsigned long long* counters = nullptr; int counters_cap = 0;
     unsigned short* stk_g = nullptr; size_t stk_cap = 0;  // regroup layout: attenuation stacks [level][slot]
+    // wavefront layout: path records (two arrays), per-material queues, free stack slots, counters
+    WfRec* wf_rec = nullptr; size_t wf_rec_cap = 0;
+    unsigned* wf_queue = nullptr; size_t wf_queue_cap = 0;
+    unsigned* wf_free = nullptr; size_t wf_free_cap = 0;
+    WfCounters* wf_cnt = nullptr; size_t wf_cnt_cap = 0;
+    unsigned* wf_host = nullptr;  // pinned: n_in read back every few bounces
     // PNG encoder work buffers (tray_encode_png), kept between calls
     unsigned char* png_filt = nullptr; size_t png_filt_cap = 0;
     unsigned char* png_out = nullptr; size_t png_out_cap = 0;
@@ -295,16 +302,68 @@ struct TraceLaunch {
     }
 };
 
+// Wavefront layout: the host drives one bounce at a time (intersect, shade, regenerate, advance) until no path is left.
+constexpr unsigned kWfCap = 1u << 21;  // paths in flight (records: 2 x 201 MB)
+int launch_trace_wavefront(Device& d, const TraceArgs& A, const DevScene<double>& S) {
+    const unsigned cap = (unsigned)std::min<unsigned long long>(kWfCap, (A.n_samples + kWfTPB - 1) / kWfTPB * kWfTPB);
+    grow(d.wf_rec, d.wf_rec_cap, (size_t)2 * cap);
+    grow(d.wf_queue, d.wf_queue_cap, (size_t)4 * cap);
+    grow(d.wf_free, d.wf_free_cap, (size_t)cap);
+    grow(d.wf_cnt, d.wf_cnt_cap, (size_t)1);
+    grow(d.stk_g, d.stk_cap, (size_t)cap * (size_t)A.max_depth);
+    if (!d.wf_host) CK(cudaHostAlloc(&d.wf_host, sizeof(unsigned), cudaHostAllocDefault));
+    WfArgs W;
+    W.A = A; W.A.stk_g = d.stk_g; W.A.n_slots = cap;
+    W.cur = d.wf_rec; W.next = d.wf_rec + cap; W.queue = d.wf_queue; W.freelist = d.wf_free; W.cnt = d.wf_cnt; W.cap = cap;
+    const unsigned grid = cap / kWfTPB;
+    const size_t smem = (size_t)S.n_pad * 16 + 256 + (size_t)kCand * kWfTPB * sizeof(uint16_t);
+    CK(cudaFuncSetAttribute(wf_intersect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, wf_intersect_kernel<false>, kWfTPB, smem));
+    const unsigned grid_int = (unsigned)std::min<unsigned long long>((unsigned long long)d.num_sms * std::max(1, bps), (cap + kWfTPB - 1) / kWfTPB);
+    int launches = 0;
+    wf_init_kernel<<<(cap + 255) / 256, 256, 0, d.stream>>>(W);
+    wf_regen_kernel<<<grid, kWfTPB, 0, d.stream>>>(W);
+    wf_advance_kernel<<<1, 1, 0, d.stream>>>(W.cnt);
+    std::swap(W.cur, W.next);
+    launches += 3;
+    for (int bounce = 1;; bounce++) {
+        wf_intersect_kernel<false><<<grid_int, kWfTPB, smem, d.stream>>>(W, S);
+        wf_shade_kernel<<<grid, kWfTPB, 0, d.stream>>>(W, S);
+        wf_regen_kernel<<<grid, kWfTPB, 0, d.stream>>>(W);
+        wf_advance_kernel<<<1, 1, 0, d.stream>>>(W.cnt);
+        std::swap(W.cur, W.next);
+        launches += 4;
+        if (bounce % 8 == 0) {
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(d.wf_host, &W.cnt->n_in, sizeof(unsigned), cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaStreamSynchronize(d.stream));
+            if (*d.wf_host == 0) break;
+        }
+        if (bounce > 100000000) throw std::runtime_error("wavefront: no progress");
+    }
+    CK(cudaGetLastError());
+    return launches;
+}
+
 #ifndef TRAY_DEFAULT_LAYOUT
 #define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_REGROUP  // measured: 103.1 ms vs 107.9 ms plain on config 2 (profiles/r01_*)
 #endif
-void launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precision, int accel, int layout) {
+int launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precision, int accel, int layout) {
     const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
-    const bool regroup = (layout == TRAY_LAYOUT_AUTO ? TRAY_DEFAULT_LAYOUT : layout) == TRAY_LAYOUT_REGROUP;
+    if (layout == TRAY_LAYOUT_AUTO) layout = TRAY_DEFAULT_LAYOUT;
+    if (layout == TRAY_LAYOUT_WAVEFRONT) {
+        const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
+        if (precision == TRAY_FP64_STRICT && !bvh && (size_t)d.n_pad * 16 + tail <= kSmemBudget)
+            return launch_trace_wavefront(d, A, dev_scene<double>(ctx, d));
+        layout = TRAY_LAYOUT_REGROUP;
+    }
+    const bool regroup = layout == TRAY_LAYOUT_REGROUP;
     if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh, regroup);
     else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
+    return 1;
 }
 
 // ---- host BVH build: median split on the longest centroid axis, <= 4 spheres per leaf ----------------------
@@ -460,6 +519,8 @@ void tray_destroy(tray_ctx* ctx) {
         cudaStreamSynchronize(d.stream);
         free_scene(d);
         cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g);
+        cudaFree(d.wf_rec); cudaFree(d.wf_queue); cudaFree(d.wf_free); cudaFree(d.wf_cnt);
+        if (d.wf_host) cudaFreeHost(d.wf_host);
         cudaFree(d.png_filt); cudaFree(d.png_out); cudaFree(d.png_hist); cudaFree(d.png_piece); cudaFree(d.png_adler); cudaFree(d.png_blocks); cudaFree(d.png_tot); cudaFree(d.stats); cudaFree(d.srgb_thr);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -607,7 +668,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
     if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP64_STRICT_BRUTE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
     if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_BVH) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
-    if (p->layout < TRAY_LAYOUT_AUTO || p->layout > TRAY_LAYOUT_REGROUP) return fail(ctx, TRAY_E_INVALID, "tray_render: bad layout");
+    if (p->layout < TRAY_LAYOUT_AUTO || p->layout > TRAY_LAYOUT_WAVEFRONT) return fail(ctx, TRAY_E_INVALID, "tray_render: bad layout");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
     if (p->sums_mode < TRAY_SUMS_OFF || p->sums_mode > TRAY_SUMS_ACCUMULATE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad sums_mode");
@@ -734,7 +795,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
                     A.stk_g = nullptr; A.n_slots = 0;
                     CK(cudaEventRecord(next_event(d), d.stream));
-                    launch_trace(ctx, d, A, p->precision, p->accel, p->layout);
+                    launches += launch_trace(ctx, d, A, p->precision, p->accel, p->layout) - 1;
                     CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;

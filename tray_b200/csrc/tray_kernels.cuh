@@ -184,6 +184,90 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
     }
 }
 
+// Closest hit of one ray per lane behind the exact fp32 pre-filter: scans the pair table in shared memory, queues the
+// survivors in this lane's candidate list (flushing it through the exact test when it is about to overflow). The caller
+// resolves what is left in the list. Shared by the megakernel and the wavefront intersect kernel.
+template <typename T, bool FMA, int TPB>
+__device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* sfp, const typename Vec4T<T>::type* __restrict__ ggeo,
+                                    uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a,
+                                    T& best_t, int& best, int& ncand, unsigned& mask_prev) {
+    constexpr int CH = TRAY_CH;
+    const int n_pad = S.n_pad;
+    // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction, 8 instructions per pair) ----
+    // A test is skipped only when the fp32 evaluation PROVES that Sphere.Hit returns false in strict fp64
+    // ("exact pre-filter"). Per sphere, with d = D/|D|, h~ = d.(C-O), c = |C-O|^2 - r^2 and the
+    // table holding (C, -(|C|^2 - r^2)):
+    //   hp ~ h~ + EH = d.C - d.O + EH        (3 FMA)      |hp - (h~ + EH)| <= Eh = 16u R < EH,   R = max|C|inf + |O|inf
+    //   nc ~ -c + E                          (1 ADD + 3 FMA, expanded as -(|C|^2 - r^2) - |O|^2 + 2 O.C + E)
+    //   v1 = hp*hp + nc                      (1 FMA)      errors of nc and of this rounding <= u (22 R^2 + 6.2 max r^2) < E
+    //   v1 < 0 :  h~ >= 0  =>  hp >= h~ >= 0, so h~^2 - c <= hp^2 - c < 0: disc < 0 in exact and in fp64 arithmetic
+    //             h~ <  0  =>  c > hp^2 + (E - error) > 0: h < 0 < c, both roots <= 0 (or disc < 0)
+    //   hp < 0 and nc < 0  =>  h~ < 0 < c as well
+    // Everything else (incl. NaN table entries = spheres outside the filter's range, canonical NaN has sign 0)
+    // goes to the exact path.
+    const float u32 = 5.9604645e-8f;
+    const double inv_n = 1.0 / sqrt((double)a);
+    const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
+    const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+    float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+    const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+    const float R = S.filt_mc + mo;
+    float eh = 17.5f * u32 * R;                                             // > 1.01 * Eh
+    float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+                         ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));  // E - |O|^2
+    if (!(mo < 1e6f)) { noot = __int_as_float(0x7f800000); eh = 0.0f; }     // origin too far out: filter off for this ray
+    ndo += eh;                                                              // one more rounding <= u(|d.O| + EH), inside Eh
+    const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
+    const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
+    const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
+    const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
+    // Software-pipelined by half chunks: while the two pairs in registers A are evaluated, the LDS.128 of the next
+    // two pairs (B) are in flight, and vice versa; the table is followed by other shared data, so the last prefetch
+    // reads valid (unused) memory. One running shared-memory address, immediate offsets.
+    static_assert(CH == 8, "the pre-filter loop is written for chunks of 8 spheres");
+    auto lds4 = [](float4& v, unsigned addr) {
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    };
+    unsigned mask = 0;
+    auto pair = [&](const float4& g0, const float4& g1) {
+        const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
+        float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
+        float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);                    // -(|C|^2 - r^2) - |O|^2 + E
+        float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
+        float2 v1 = __ffma2_rn(h, h, nc);
+        int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
+        int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
+        mask = __funnelshift_l((unsigned)mx, mask, 1);
+        mask = __funnelshift_l((unsigned)my, mask, 1);
+    };
+    unsigned saddr = (unsigned)__cvta_generic_to_shared(sfp);
+    float4 a0, a1, a2, a3, b0, b1, b2, b3;
+    lds4(a0, saddr); lds4(a1, saddr + 16); lds4(a2, saddr + 32); lds4(a3, saddr + 48);
+#pragma unroll 1
+    for (int i = 0; i < n_pad; i += CH) {
+        lds4(b0, saddr + 64); lds4(b1, saddr + 80); lds4(b2, saddr + 96); lds4(b3, saddr + 112);
+        mask = 0;
+        pair(a0, a1); pair(a2, a3);
+        lds4(a0, saddr + 128); lds4(a1, saddr + 144); lds4(a2, saddr + 160); lds4(a3, saddr + 176);
+        pair(b0, b1); pair(b2, b3);
+        saddr += 128;
+        mask = ~mask & 0xffu;  // 1 = must be tested exactly
+        if (mask_prev) {
+            if (ncand > kCand - CH) {  // list about to overflow (rare): run the exact test on what is queued
+                push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+            }
+            unsigned m = mask_prev;
+            do {  // append in index order: bit CH-1-u <-> sphere (i-CH)+u
+                int bit = 31 - __clz(m);
+                cand[ncand * TPB] = (uint16_t)(i - 1 - bit);
+                ncand++;
+                m &= ~(1u << bit);
+            } while (m);
+        }
+        mask_prev = has ? mask : 0u;  // idle lanes queue nothing
+    }
+}
+
 // Exchange area of the regroup layout (one per CTA, shared memory): the path state of every lane, SoA.
 template <int TPB>
 struct RegroupBuf {
@@ -294,79 +378,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
             if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
         } else if constexpr (GEO == kGeoFilter) {
-            // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction, 8 instructions per pair) ----
-            // A test is skipped only when the fp32 evaluation PROVES that Sphere.Hit returns false in strict fp64
-            // ("exact pre-filter"). Per sphere, with d = D/|D|, h~ = d.(C-O), c = |C-O|^2 - r^2 and the
-            // table holding (C, -(|C|^2 - r^2)):
-            //   hp ~ h~ + EH = d.C - d.O + EH        (3 FMA)      |hp - (h~ + EH)| <= Eh = 16u R < EH,   R = max|C|inf + |O|inf
-            //   nc ~ -c + E                          (1 ADD + 3 FMA, expanded as -(|C|^2 - r^2) - |O|^2 + 2 O.C + E)
-            //   v1 = hp*hp + nc                      (1 FMA)      errors of nc and of this rounding <= u (22 R^2 + 6.2 max r^2) < E
-            //   v1 < 0 :  h~ >= 0  =>  hp >= h~ >= 0, so h~^2 - c <= hp^2 - c < 0: disc < 0 in exact and in fp64 arithmetic
-            //             h~ <  0  =>  c > hp^2 + (E - error) > 0: h < 0 < c, both roots <= 0 (or disc < 0)
-            //   hp < 0 and nc < 0  =>  h~ < 0 < c as well
-            // Everything else (incl. NaN table entries = spheres outside the filter's range, canonical NaN has sign 0)
-            // goes to the exact path.
-            const float u32 = 5.9604645e-8f;
-            const double inv_n = 1.0 / sqrt((double)a);
-            const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
-            const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
-            float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
-            const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
-            const float R = S.filt_mc + mo;
-            float eh = 17.5f * u32 * R;                                             // > 1.01 * Eh
-            float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
-                                 ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));  // E - |O|^2
-            if (!(mo < 1e6f)) { noot = __int_as_float(0x7f800000); eh = 0.0f; }     // origin too far out: filter off for this ray
-            ndo += eh;                                                              // one more rounding <= u(|d.O| + EH), inside Eh
-            const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
-            const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
-            const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
-            const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
-            // Software-pipelined by half chunks: while the two pairs in registers A are evaluated, the LDS.128 of the next
-            // two pairs (B) are in flight, and vice versa; the table is followed by other shared data, so the last prefetch
-            // reads valid (unused) memory. One running shared-memory address, immediate offsets.
-            static_assert(CH == 8, "the pre-filter loop is written for chunks of 8 spheres");
-            auto lds4 = [](float4& v, unsigned addr) {
-                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-            };
-            unsigned mask = 0;
-            auto pair = [&](const float4& g0, const float4& g1) {
-                const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
-                float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
-                float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);                    // -(|C|^2 - r^2) - |O|^2 + E
-                float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
-                float2 v1 = __ffma2_rn(h, h, nc);
-                int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
-                int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
-                mask = __funnelshift_l((unsigned)mx, mask, 1);
-                mask = __funnelshift_l((unsigned)my, mask, 1);
-            };
-            unsigned saddr = (unsigned)__cvta_generic_to_shared(sfp);
-            float4 a0, a1, a2, a3, b0, b1, b2, b3;
-            lds4(a0, saddr); lds4(a1, saddr + 16); lds4(a2, saddr + 32); lds4(a3, saddr + 48);
-#pragma unroll 1
-            for (int i = 0; i < n_pad; i += CH) {
-                lds4(b0, saddr + 64); lds4(b1, saddr + 80); lds4(b2, saddr + 96); lds4(b3, saddr + 112);
-                mask = 0;
-                pair(a0, a1); pair(a2, a3);
-                lds4(a0, saddr + 128); lds4(a1, saddr + 144); lds4(a2, saddr + 160); lds4(a3, saddr + 176);
-                pair(b0, b1); pair(b2, b3);
-                saddr += 128;
-                mask = ~mask & 0xffu;  // 1 = must be tested exactly
-                if (mask_prev) {
-                    if (ncand > kCand - CH) {  // list about to overflow (rare): run the exact test on what is queued
-                        push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
-                    }
-                    unsigned m = mask_prev;
-                    do {  // append in index order: bit CH-1-u <-> sphere (i-CH)+u
-                        int bit = 31 - __clz(m);
-                        cand[ncand * TPB] = (uint16_t)(i - 1 - bit);
-                        ncand++;
-                        m &= ~(1u << bit);
-                    } while (m);
-                }
-                mask_prev = has ? mask : 0u;  // idle lanes queue nothing
-            }
+            filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
         } else {
         // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
         // shift. The mask of chunk k is examined while chunk k+1 is in flight, so no branch waits on FP64 results.
