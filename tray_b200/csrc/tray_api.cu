@@ -202,7 +202,7 @@ template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device
 template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& d) {
     DevScene<float> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
-    s.fpair = nullptr; s.filt_mc = 0; s.filt_r2max = 0;
+    s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
     s.bvh = nullptr; s.bvh_leaf_ids = nullptr; s.bvh_always = nullptr; s.bvh_n_always = 0; s.bvh_extent = 0;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
@@ -279,12 +279,12 @@ struct TraceLaunch {
                 launch_trace_geo<T, FMA, kGeoBVH>(d, A, S, none, tail);
                 return;
             }
-            if (filter && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
-                if (regroup) { launch_trace_regroup<T, FMA>(d, A, S, (size_t)S.n_pad * 16 + tail); return; }
-                GeoArg<T, kGeoFilter> none{};
-                launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
-                return;
-            }
+        }
+        if (filter && S.fpair && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
+            if (regroup) { launch_trace_regroup<T, FMA>(d, A, S, (size_t)S.n_pad * 16 + tail); return; }
+            GeoArg<T, kGeoFilter> none{};
+            launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
+            return;
         }
         if (TRAY_PARAM_GEO && S.n_pad <= kParamSpheres) {
             // small scene: the table travels in the kernel parameters (constant bank, uniform loads)
@@ -362,7 +362,8 @@ int launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precisi
     if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh, regroup);
     else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
-    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data());
+    // fp32 fast path: the same conservative pre-filter (it proves a miss in exact arithmetic), survivors tested in fp32
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, false, regroup);
     return 1;
 }
 
