@@ -443,3 +443,65 @@ def test_cpp_benchmark_cli_matches_python_host(ctx, tmp_path):
     t = tracer(96, 54, 4, 20)
     img = t.Render(ray.RichScene(rand.New(2)))
     assert np.array_equal(rgb, img[:, :, :3])
+
+
+# ---- soundness of the exact fp32 pre-filter: it may only skip a test that strict fp64 would fail -----------------------
+def _random_scene(rs, n, scale, shift):
+    """n random spheres of mixed materials: overlapping, nested, tangent, grazing sizes; coordinates up to `scale` (the
+    filter's table takes |C| <= 256 and r^2 <= 256, larger ones go to the exact path), the whole scene moved by `shift`."""
+    objs = []
+    for i in range(n):
+        c = (rs.uniform(-1, 1, 3) * scale + shift).tolist()
+        r = float(abs(rs.normal(0.0, 0.15 * scale)) + 1e-3 * scale)
+        if i % 7 == 3:
+            r = float(scale * rs.choice([1e-4, 0.5, 3.0, 40.0]))
+        k = rs.randint(3)
+        mat = (ray.Lambertian(rs.uniform(0.1, 1, 3)), ray.Metal(rs.uniform(0.3, 1, 3), float(rs.choice([0.0, 0.3, 1.5]))),
+               ray.Dielectric(float(rs.choice([1.5, 1.0 / 1.5, 2.4]))))[k]
+        objs.append(ray.Sphere(c, r, mat))
+        if i % 5 == 0:  # an exact duplicate (ties -> lowest index) and a concentric shell (back-face hits)
+            objs.append(ray.Sphere(c, r, ray.Metal((0.9, 0.9, 0.9), 0.0)))
+            objs.append(ray.Sphere(c, r * 0.9, ray.Dielectric(1.5)))
+    return ray.Scene(objs, ray.DefaultBackground())
+
+
+@pytest.mark.parametrize("seed,n,scale,shift", [(1, 40, 1.0, 0.0), (2, 150, 5.0, 3.0), (3, 500, 30.0, -100.0), (4, 60, 200.0, 0.0),
+                                                 (5, 30, 1e-3, 0.0), (6, 90, 3.0, 250.0), (7, 700, 12.0, 0.0), (8, 25, 1e4, 0.0)])
+def test_prefilter_never_changes_a_result_on_random_scenes(ctx, seed, n, scale, shift):
+    """Images, linear-HDR means and segment counts of the default kernel (pre-filter, regroup layout), of the plain and
+    wavefront layouts and of the BVH must equal the all-fp64 linear scan bit for bit, whatever the scene looks like --
+    including cameras inside spheres, spheres beyond the filter's table range and origins far from the scene."""
+    rs = np.random.RandomState(seed)
+    scene = _random_scene(rs, n, scale, shift)
+    w, h, spp, depth = 96, 54, 4, 20
+    look = np.full(3, shift, dtype=float)
+    cam = ray.Camera(Position=tuple(look + rs.uniform(-1.5, 1.5, 3) * scale), LookAt=tuple(look), VerticalFoV=60.0,
+                     Aperture=0.05 * scale if seed % 2 else 0.0, FocalLength=scale, FocusDistance=scale)
+    outs = {}
+    for name, precision, layout, accel in (("brute", ray.FP64_STRICT_BRUTE, ray.LAYOUT_PLAIN, ray.ACCEL_BRUTE),
+                                           ("filter+regroup", ray.FP64_STRICT, ray.LAYOUT_REGROUP, ray.ACCEL_BRUTE),
+                                           ("filter+plain", ray.FP64_STRICT, ray.LAYOUT_PLAIN, ray.ACCEL_BRUTE),
+                                           ("wavefront", ray.FP64_STRICT, ray.LAYOUT_WAVEFRONT, ray.ACCEL_BRUTE),
+                                           ("bvh", ray.FP64_STRICT, ray.LAYOUT_AUTO, ray.ACCEL_BVH)):
+        t = tracer(w, h, spp, depth, seed=seed, precision=precision, cam=cam)
+        t.RayRadius = 0.5
+        t.Layout, t.Accel = layout, accel
+        img = t.Render(scene).copy()
+        outs[name] = (img, ctx.read_hdr(w, h), t.Stats["segments"], t.Stats["depth_exhausted"])
+    ref = outs["brute"]
+    assert ref[2] > w * h * spp  # something was hit
+    for name, o in outs.items():
+        assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1]) and o[2:] == ref[2:], name
+
+
+def test_prefilter_random_scene_matches_oracle(ctx, O):
+    """One of the random scenes against the CPU oracle as well (the GPU modes above agree among themselves)."""
+    rs = np.random.RandomState(11)
+    scene = _random_scene(rs, 80, 4.0, 1.0)
+    w, h, spp, depth = 64, 36, 3, 20
+    cam = ray.Camera(Position=(6.0, 2.0, 7.0), LookAt=(1.0, 1.0, 1.0), VerticalFoV=50.0, Aperture=0.2, FocalLength=5.0, FocusDistance=8.0)
+    t = tracer(w, h, spp, depth, seed=9, cam=cam)
+    img = t.Render(scene).copy()
+    ref, hdr, st = O.render(oracle_flat(O, scene), oracle_cam(O, t),
+                            O.make_params(w, h, spp=spp, max_depth=depth, seed=9, num_workers=4, stream_mode=1), want_hdr=True)
+    assert np.array_equal(img, ref) and np.array_equal(ctx.read_hdr(w, h), hdr) and t.Stats["segments"] == st["segments"]
