@@ -505,3 +505,27 @@ def test_prefilter_random_scene_matches_oracle(ctx, O):
     ref, hdr, st = O.render(oracle_flat(O, scene), oracle_cam(O, t),
                             O.make_params(w, h, spp=spp, max_depth=depth, seed=9, num_workers=4, stream_mode=1), want_hdr=True)
     assert np.array_equal(img, ref) and np.array_equal(ctx.read_hdr(w, h), hdr) and t.Stats["segments"] == st["segments"]
+
+
+def test_cpp_tray_cli_frame_matches_python_host(ctx, O, tmp_path):
+    """tray_b200/tray = main.go's non-interactive path (-exit): image round(s*W) x round(s*2H), Render, -save, downscale and
+    half-block frame on the device. Its stdout must be the frame the Python host produces for the same flags."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tray_b200", "tray")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    out = str(tmp_path / "t.png")
+    for s, cols, rows in ((4, 40, 12), (0.5, 40, 12), (1, 32, 9)):
+        r = subprocess.run([exe, "-exit", "-seed", "2", "-s", str(s), "-r", "4", "-d", "12", "-cols", str(cols), "-rows", str(rows), "-save", out],
+                           capture_output=True, timeout=120)
+        assert r.returncode == 0, r.stderr.decode()
+        w, h = int(round(s * cols)), int(round(s * rows * 2))
+        t = tracer(w, h, 4, 12)
+        img = t.Render(ray.RichScene(rand.New(2))).copy()
+        ansi, small, _ = ctx.present(cols, rows * 2)
+        assert r.stdout == ansi
+        want = img if s == 1 else (O.nn_scale(img, cols, rows * 2) if s < 1 else O.bilinear_scale(img, cols, rows * 2))
+        assert np.array_equal(small, want)
+        from test_gpu_png import parse_png
+        rgb, _, _, _ = parse_png(open(out, "rb").read())
+        assert np.array_equal(rgb, img[:, :, :3])

@@ -189,6 +189,17 @@ class Tracer : public Camera {  // ray/tracer.go:25-35
     void RenderLines(int idx, int yStart, int yEnd, Scene& scene) { run(scene, yStart, yEnd, idx, 0); }
     RGBA& Image() { return imageData_; }
     uint64_t Progress() const { return ctx_ ? tray_progress(ctx_) : 0; }
+    // The tail of tray's OnResize (main.go:119-130) on the device: the last frame scaled to cols x 2*rows pixels and
+    // emitted as the half-block truecolor frame of a cols x rows terminal (write it to the terminal as is).
+    std::string Present(int cols, int rows, double* device_ms = nullptr) {
+        if (!ctx_) throw std::runtime_error("Present: nothing rendered");
+        std::string out((size_t)rows * ((size_t)cols * 41 + 5), '\0');
+        size_t n = 0;
+        check(tray_present(ctx_, cols, 2 * rows, nullptr, reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n, device_ms));
+        out.resize(n);
+        return out;
+    }
+    int Layout = TRAY_LAYOUT_AUTO;
     // SaveImage(img, fname) (main.go:26-36, benchmark/benchmark.go:23-33): the PNG file of the last frame, encoded on the
     // device from the frame still resident in HBM. Returns the device time of the encode in ms.
     double SaveImage(const std::string& fname) {
@@ -238,7 +249,7 @@ class Tracer : public Camera {  // ray/tracer.go:25-35
         uint64_t seed = Seed;
         if (seed == 0) { std::random_device rd; seed = (((uint64_t)rd() << 32) | rd()) | 1; }  // tracer.go:32
         p.seed = seed; p.y0 = y0; p.y1 = y1; p.stream_mode = StreamMode; p.num_workers = workers; p.stream_idx = stream_idx;
-        p.precision = Precision; p.split_mode = SplitMode;
+        p.precision = Precision; p.split_mode = SplitMode; p.layout = Layout;
         check(tray_render(ctx_, &c, &p, imageData_.Pix.data(), (size_t)imageData_.Stride, &Stats));
     }
     int width_, height_;
