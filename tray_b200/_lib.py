@@ -65,6 +65,11 @@ def build_library(force=False, verbose=False):
     srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "tray_wavefront.cuh", "zig_tables.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "tray_cuda.h"))
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    # the C++ host CLIs (the reference's two mains on this backend) are built by the same Makefile
+    host = [os.path.join(_HERE, "host", f) for f in ("tray.hpp", "benchmark.cpp", "tray.cpp")]
+    for exe in ("benchmark", "tray"):
+        e = os.path.join(_HERE, exe)
+        stale = stale or not os.path.exists(e) or any(os.path.getmtime(s) > os.path.getmtime(e) for s in host)
     if force or stale:
         cmd = ["make", "-C", os.path.join(_HERE, "csrc")] + (["-B"] if force else [])
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
