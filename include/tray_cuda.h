@@ -68,7 +68,7 @@ extern "C" {
 /* closest-hit structure. Results are identical for all of them (ties resolve to the lowest index). */
 #define TRAY_ACCEL_AUTO 0  /* brute force up to 2048 spheres, BVH above */
 #define TRAY_ACCEL_BRUTE 1 /* linear scan of the sphere table (the reference's Scene.Hit order) */
-#define TRAY_ACCEL_BVH 2   /* small BVH (median split, <= 4 spheres per leaf) built on the host at upload */
+#define TRAY_ACCEL_BVH 2   /* small BVH (<= 4 spheres per leaf), built at upload on the host (median split) or on the device (LBVH) */
 
 /* divergence layout of the trace kernel. Results are identical for all of them. */
 #define TRAY_LAYOUT_AUTO 0
@@ -157,6 +157,17 @@ TRAY_API int tray_init(const int *devices, int n_devices, tray_ctx **out);
 TRAY_API void tray_destroy(tray_ctx *ctx);
 TRAY_API const char *tray_last_error(tray_ctx *ctx); /* ctx may be NULL: last init error */
 TRAY_API int tray_abi_version(void);
+
+/* Context options. TRAY_CFG_BVH_BUILD: where tray_scene_upload builds the closest-hit BVH (results are identical for any
+ * tree): AUTO = LBVH on the device from 1024 spheres up, host median split below; the device build falls back to the
+ * host when its radix tree would be deeper than the traversal stack. tray_query(TRAY_CFG_BVH_BUILD) tells what the last
+ * upload did (1 = built on the device). */
+#define TRAY_CFG_BVH_BUILD 1
+#define TRAY_BVH_BUILD_AUTO 0
+#define TRAY_BVH_BUILD_HOST 1
+#define TRAY_BVH_BUILD_DEVICE 2
+TRAY_API int tray_configure(tray_ctx *ctx, int32_t key, int64_t value);
+TRAY_API int64_t tray_query(tray_ctx *ctx, int32_t key);
 
 /* Copies the scene to every device of the context. May be called again to replace the scene. */
 TRAY_API int tray_scene_upload(tray_ctx *ctx, const tray_scene_desc *scene);

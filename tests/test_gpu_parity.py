@@ -529,3 +529,40 @@ def test_cpp_tray_cli_frame_matches_python_host(ctx, O, tmp_path):
         from test_gpu_png import parse_png
         rgb, _, _, _ = parse_png(open(out, "rb").read())
         assert np.array_equal(rgb, img[:, :, :3])
+
+
+# ---- the BVH built on the device (LBVH) gives the same bits as the host build and the linear scan ------
+@pytest.mark.parametrize("kind", ["rich10k", "random", "ties", "cluster", "tiny"])
+def test_device_lbvh_build_matches_host_build_and_scan(kind):
+    from tray_b200 import _lib
+    rs = np.random.RandomState(3)
+    if kind == "rich10k":
+        scene, cam, w, h = ray.RichScene(rand.New(2), half=50), ray.RichSceneCamera(), 160, 90
+    elif kind == "random":
+        scene, cam, w, h = _random_scene(rs, 1500, 20.0, 5.0), ray.Camera(Position=(30, 20, 40), LookAt=(5, 5, 5), VerticalFoV=50.0), 96, 54
+    elif kind == "ties":
+        L = ray.Lambertian((.8, .7, .6))
+        objs = [ray.Sphere((0, 0, -3), .5, ray.Metal((.9, .9, .9), 0.1))] * 40 + [ray.Sphere((0.01 * i, 0.2, -4), .3, L) for i in range(30)]
+        scene, cam, w, h = ray.Scene(objs + [ray.Sphere((0, -100.5, -3), 100, L)], ray.DefaultBackground()), ray.Camera(VerticalFoV=40.0), 64, 36
+    elif kind == "cluster":  # thousands of centres inside one Morton cell plus far outliers: keys differ in the id bits only
+        objs = [ray.Sphere((1e-7 * rs.rand(), 1e-7 * rs.rand(), -5 + 1e-7 * rs.rand()), 0.5 + 0.3 * rs.rand(), ray.Dielectric(1.5) if i % 2 else ray.Lambertian((.5, .6, .7)))
+                for i in range(1200)] + [ray.Sphere((50, 0, -60), 1.0, ray.Metal((.9, .9, .9), 0.0)), ray.Sphere((-50, 3, -60), 1.0, ray.Lambertian((.9, .2, .2)))]
+        scene, cam, w, h = ray.Scene(objs, ray.DefaultBackground()), ray.Camera(VerticalFoV=70.0), 64, 36
+    else:
+        scene, cam, w, h = ray.DefaultScene(), ray.Camera(Position=(-2, 2, 1), LookAt=(0, 0, -1), VerticalFoV=20.0), 64, 36
+    outs = {}
+    for name, build, accel in (("scan", _lib.BVH_BUILD_HOST, ray.ACCEL_BRUTE), ("host", _lib.BVH_BUILD_HOST, ray.ACCEL_BVH),
+                               ("device", _lib.BVH_BUILD_DEVICE, ray.ACCEL_BVH)):
+        c = ray.Context([0])
+        c.configure(_lib.CFG_BVH_BUILD, build)
+        t = tracer(w, h, 3, 12, cam=cam)
+        t.Context, t.Accel = c, accel
+        img = t.Render(scene).copy()
+        outs[name] = (img, c.read_hdr(w, h), t.Stats["segments"], c.query(_lib.CFG_BVH_BUILD), t.Stats["sphere_tests"])
+        c.close()
+    assert outs["device"][3] == 1 and outs["host"][3] == 0
+    for name in ("host", "device"):
+        assert np.array_equal(outs[name][0], outs["scan"][0]) and np.array_equal(outs[name][1], outs["scan"][1]) and outs[name][2] == outs["scan"][2], name
+    if kind in ("rich10k", "random"):
+        assert outs["device"][4] < 2.5 * outs["host"][4] and outs["device"][4] < outs["scan"][4] / 4  # it culls about as well as the host's
+        print(kind, "sphere tests per segment: host %.2f device %.2f" % (outs["host"][4] / outs["host"][2], outs["device"][4] / outs["device"][2]))

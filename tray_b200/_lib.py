@@ -15,10 +15,11 @@ SPLIT_TILES, SPLIT_SAMPLES = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
 SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
 LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, LAYOUT_WAVEFRONT = 0, 1, 2, 3
+CFG_BVH_BUILD, BVH_BUILD_AUTO, BVH_BUILD_HOST, BVH_BUILD_DEVICE = 1, 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
-           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png")
+           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png", "tray_configure", "tray_query")
 
 
 class TrayError(RuntimeError):
@@ -62,7 +63,7 @@ def library_path():
 
 def build_library(force=False, verbose=False):
     """Compile libtraycuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "tray_wavefront.cuh", "zig_tables.h")]
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("tray_api.cu", "tray_kernels.cuh", "tray_device.cuh", "tray_png.cuh", "tray_wavefront.cuh", "tray_lbvh.cuh", "zig_tables.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "tray_cuda.h"))
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     # the C++ host CLIs (the reference's two mains on this backend) are built by the same Makefile
@@ -111,6 +112,9 @@ def lib():
         L.tray_png_bound.argtypes = [C.c_int32, C.c_int32]
         L.tray_png_bound.restype = C.c_size_t
         L.tray_encode_png.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
+        L.tray_configure.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+        L.tray_query.argtypes = [C.c_void_p, C.c_int32]
+        L.tray_query.restype = C.c_int64
         L.tray_progress.argtypes = [C.c_void_p]
         L.tray_progress.restype = C.c_uint64
         L.tray_measure_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -17,6 +17,7 @@
 #include "tray_kernels.cuh"
 #include "tray_png.cuh"
 #include "tray_wavefront.cuh"
+#include "tray_lbvh.cuh"
 
 using namespace tray;
 
@@ -110,6 +111,10 @@ struct Device {
     double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
     unsigned long long* counters = nullptr; int counters_cap = 0;
     unsigned short* stk_g = nullptr; size_t stk_cap = 0;  // regroup layout: attenuation stacks [level][slot]
+    // LBVH build scratch (tray_lbvh.cuh), kept between uploads
+    unsigned long long* lbvh_keys = nullptr; size_t lbvh_keys_cap = 0;
+    int* lbvh_int = nullptr; size_t lbvh_int_cap = 0;
+    int2* lbvh_int2 = nullptr; size_t lbvh_int2_cap = 0;
     // wavefront layout: path records (two arrays), per-material queues, free stack slots, counters
     WfRec* wf_rec = nullptr; size_t wf_rec_cap = 0;
     unsigned* wf_queue = nullptr; size_t wf_queue_cap = 0;
@@ -164,6 +169,8 @@ struct tray_ctx {
     int width = 0, height = 0, y0 = 0, y1 = 0;
     bool have_image = false, have_hdr = false;
     int split_mode = 0;
+    int bvh_build = TRAY_BVH_BUILD_AUTO;  // tray_configure(TRAY_CFG_BVH_BUILD)
+    int bvh_built_on_device = 0;          // what the last upload did (tray_query)
     bool hdr_is_sums = false;          // last render left raw colour sums (sums_mode != 0)
     uint64_t sums_samples = 0;         // samples per pixel accumulated in them
     int sums_key[6] = {0, 0, 0, 0, 0, 0};  // geometry the sums belong to (w, h, y0, y1, shard_index, shard_count)
@@ -423,7 +430,13 @@ int bvh_build_rec(const tray_scene_desc* sc, HostBvh& b, std::vector<int>& ids, 
     return me;
 }
 
-HostBvh bvh_build(const tray_scene_desc* sc) {
+// Which spheres go into the tree (ids) and which are always tested (b.always).
+HostBvh bvh_classify(const tray_scene_desc* sc, std::vector<int>& ids);
+void bvh_build_host(const tray_scene_desc* sc, HostBvh& b, std::vector<int>& ids) {
+    if (!ids.empty()) bvh_build_rec(sc, b, ids, 0, (int)ids.size(), 1);
+    if (b.max_depth > 40) throw std::runtime_error("tray_scene_upload: BVH deeper than the traversal stack");
+}
+HostBvh bvh_classify(const tray_scene_desc* sc, std::vector<int>& ids) {
     HostBvh b;
     int n = sc->n;
     if (n == 0) return b;
@@ -433,14 +446,61 @@ HostBvh bvh_build(const tray_scene_desc* sc) {
     std::vector<double> sorted = rs;
     std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
     const double med = sorted[n / 2];
-    std::vector<int> ids;
     for (int i = 0; i < n; i++) {
         bool finite = std::isfinite(sc->cx[i]) && std::isfinite(sc->cy[i]) && std::isfinite(sc->cz[i]) && std::isfinite(rs[i]);
         if (!finite || rs[i] > 16.0 * med + 1e-300) b.always.push_back(i); else ids.push_back(i);
     }
-    if (!ids.empty()) bvh_build_rec(sc, b, ids, 0, (int)ids.size(), 1);
-    if (b.max_depth > 40) throw std::runtime_error("tray_scene_upload: BVH deeper than the traversal stack");
+    for (int i : ids) {  // max |coordinate| of the tree's boxes (the traversal stops culling for origins absurdly far away)
+        double r = rs[i];
+        b.extent = std::max(b.extent, std::max(std::fabs(sc->cx[i]) + r, std::max(std::fabs(sc->cy[i]) + r, std::fabs(sc->cz[i]) + r)) * 1.000001 + 1e-9);
+    }
     return b;
+}
+
+// LBVH on the device (tray_lbvh.cuh). Needs d.geo_d / d.radius_d uploaded. Returns false when the radix tree came out
+// deeper than the traversal stack allows (heavily clustered centres): the caller then uses the host's median-split build.
+bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<int>& ids) {
+    const int m = (int)ids.size();
+    LbvhArgs L;
+    L.m = m; L.geo = d.geo_d; L.radius = d.radius_d;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i : ids) {
+        const double c[3] = {sc->cx[i], sc->cy[i], sc->cz[i]};
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], c[k]); hi[k] = std::max(hi[k], c[k]); }
+    }
+    for (int k = 0; k < 3; k++) { L.lo[k] = lo[k]; L.inv_extent[k] = hi[k] > lo[k] ? 1.0 / (hi[k] - lo[k]) : 0.0; }
+    int n_keys = 1;
+    while (n_keys < m) n_keys *= 2;
+    L.n_keys = n_keys;
+    // ids[m] | parent[2m-1] | visits[m] | depth[2m-1]
+    grow(d.lbvh_keys, d.lbvh_keys_cap, (size_t)n_keys);
+    grow(d.lbvh_int, d.lbvh_int_cap, (size_t)6 * m);
+    grow(d.lbvh_int2, d.lbvh_int2_cap, (size_t)2 * m);
+    int* d_int = d.lbvh_int;
+    CK(cudaMemsetAsync(d_int, 0, sizeof(int) * (size_t)(6 * m), d.stream));
+    CK(cudaMemcpyAsync(d_int, ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, d.stream));
+    L.keys = d.lbvh_keys;
+    L.ids = d_int; L.parent = d_int + m; L.visits = d_int + 3 * m; L.depth = d_int + 4 * m;
+    L.range = d.lbvh_int2; L.child = d.lbvh_int2 + m;
+    CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * (size_t)(2 * m - 1)));
+    CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * m));
+    L.nodes = d.bvh; L.leaf_ids = d.bvh_leaf_ids;
+    const int T = 256;
+    lbvh_keys_kernel<<<(n_keys + T - 1) / T, T, 0, d.stream>>>(L);
+    for (int k = 2; k <= n_keys; k *= 2)
+        for (int j = k / 2; j >= 1; j /= 2) lbvh_bitonic_kernel<<<(n_keys + T - 1) / T, T, 0, d.stream>>>(L.keys, n_keys, j, k);
+    if (m > 1) lbvh_tree_kernel<<<(m - 1 + T - 1) / T, T, 0, d.stream>>>(L);
+    lbvh_boxes_kernel<<<(m + T - 1) / T, T, 0, d.stream>>>(L);
+    CK(cudaGetLastError());
+    int root_depth = 0;
+    CK(cudaMemcpyAsync(&root_depth, L.depth, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if (root_depth < 1 || root_depth > 40) {
+        cudaFree(d.bvh); cudaFree(d.bvh_leaf_ids);
+        d.bvh = nullptr; d.bvh_leaf_ids = nullptr;
+        return false;
+    }
+    return true;
 }
 
 constexpr int kBandRows = 8;
@@ -520,6 +580,7 @@ void tray_destroy(tray_ctx* ctx) {
         cudaStreamSynchronize(d.stream);
         free_scene(d);
         cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g);
+        cudaFree(d.lbvh_keys); cudaFree(d.lbvh_int); cudaFree(d.lbvh_int2);
         cudaFree(d.wf_rec); cudaFree(d.wf_queue); cudaFree(d.wf_free); cudaFree(d.wf_cnt);
         if (d.wf_host) cudaFreeHost(d.wf_host);
         cudaFree(d.png_filt); cudaFree(d.png_out); cudaFree(d.png_hist); cudaFree(d.png_piece); cudaFree(d.png_adler); cudaFree(d.png_blocks); cudaFree(d.png_tot); cudaFree(d.stats); cudaFree(d.srgb_thr);
@@ -586,7 +647,13 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
             fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nk[0], nk[1]);
         }
-        HostBvh hb = bvh_build(sc);
+        std::vector<int> tree_ids;
+        HostBvh hb = bvh_classify(sc, tree_ids);
+        // LBVH on the device for large scenes (or when asked for); the host's median-split build otherwise / as fallback
+        const bool want_device = ctx->bvh_build == TRAY_BVH_BUILD_DEVICE || (ctx->bvh_build == TRAY_BVH_BUILD_AUTO && tree_ids.size() >= 1024);
+        bool host_built = false;
+        if (!want_device) { bvh_build_host(sc, hb, tree_ids); host_built = true; }
+        ctx->bvh_built_on_device = 0;
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
@@ -594,12 +661,6 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             d.n = n; d.n_pad = n_pad;
             d.filt_mc = mc; d.filt_r2max = r2max;
             d.bvh_n_always = (int)hb.always.size(); d.bvh_extent = hb.extent;
-            if (!hb.nodes.empty()) {
-                CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * hb.nodes.size()));
-                CK(cudaMemcpy(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
-                CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * hb.leaf_ids.size()));
-                CK(cudaMemcpy(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice));
-            }
             if (!hb.always.empty()) {
                 CK(cudaMalloc(&d.bvh_always, sizeof(int) * hb.always.size()));
                 CK(cudaMemcpy(d.bvh_always, hb.always.data(), sizeof(int) * hb.always.size(), cudaMemcpyHostToDevice));
@@ -615,6 +676,18 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             CK(cudaMemcpy(d.radius_f, rf.data(), sizeof(float) * n_pad, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(d.kind, kd.data(), n_pad, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
+            bool on_device = false;
+            if (want_device && !tree_ids.empty()) on_device = bvh_build_device(d, sc, tree_ids);
+            if (on_device) ctx->bvh_built_on_device = 1;
+            else {
+                if (!host_built) { std::vector<int> tmp = tree_ids; bvh_build_host(sc, hb, tmp); host_built = true; }
+                if (!hb.nodes.empty()) {
+                    CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * hb.nodes.size()));
+                    CK(cudaMemcpy(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+                    CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * hb.leaf_ids.size()));
+                    CK(cudaMemcpy(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice));
+                }
+            }
         }
         for (int i = 0; i < 3; i++) { ctx->bg_a[i] = sc->bg_a[i]; ctx->bg_b[i] = sc->bg_b[i]; }
         ctx->host_geo_d = gd; ctx->host_geo_f = gf;
@@ -910,6 +983,20 @@ int tray_read_hdr(tray_ctx* ctx, double* hdr_out) {
         }
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
+}
+
+int tray_configure(tray_ctx* ctx, int32_t key, int64_t value) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (key == TRAY_CFG_BVH_BUILD && value >= TRAY_BVH_BUILD_AUTO && value <= TRAY_BVH_BUILD_DEVICE) { ctx->bvh_build = (int)value; return TRAY_OK; }
+    return fail(ctx, TRAY_E_INVALID, "tray_configure: unknown key or value");
+}
+
+int64_t tray_query(tray_ctx* ctx, int32_t key) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (key == TRAY_CFG_BVH_BUILD) return ctx->bvh_built_on_device;
+    return -1;
 }
 
 int tray_device_sums(tray_ctx* ctx, double** device_ptr, uint64_t* n_doubles) {

@@ -321,6 +321,12 @@ class Context:
         _lib.check(self.handle, self._L.tray_encode_png(self.handle, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(ms)))
         return buf[:n.value].tobytes(), ms.value
 
+    def configure(self, key, value):
+        _lib.check(self.handle, self._L.tray_configure(self.handle, key, value))
+
+    def query(self, key):
+        return int(self._L.tray_query(self.handle, key))
+
     def progress(self):
         return int(self._L.tray_progress(self.handle))
 
