@@ -342,6 +342,8 @@ def run_ours(args):
         for name, setp, note in (
                 ("fp64, plain layout", lambda q: setattr(q, "layout", ray.LAYOUT_PLAIN),
                  "default kernel without the per-material regrouping of paths inside the CTA (TRAY_LAYOUT_PLAIN)"),
+                ("fp64, wavefront layout", lambda q: setattr(q, "layout", ray.LAYOUT_WAVEFRONT),
+                 "path state in HBM, one bounce = intersect | shade over per-material queues | regenerate kernels (TRAY_LAYOUT_WAVEFRONT)"),
                 ("fp64, bvh", lambda q: setattr(q, "accel", ray.ACCEL_BVH),
                  "small BVH instead of the linear scan (TRAY_ACCEL_BVH): far fewer sphere tests, so no roofline claim; image bit-identical")):
             p2 = tr._params(0, h)
