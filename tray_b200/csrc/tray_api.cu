@@ -105,6 +105,10 @@ struct Device {
     uint8_t* kind = nullptr; double4* params = nullptr;
     float4* fpair = nullptr; float filt_mc = 0, filt_r2max = 0;
     BvhNode* bvh = nullptr; int* bvh_leaf_ids = nullptr; int* bvh_always = nullptr; int bvh_n_always = 0; double bvh_extent = 0;
+    bool bvh_present = false;
+    // the scene buffers are kept between uploads and only grown (cudaFree / cudaMalloc per keypress cost up to tens of ms)
+    size_t cap_geo_d = 0, cap_geo_f = 0, cap_radius_d = 0, cap_radius_f = 0, cap_kind = 0, cap_params = 0, cap_fpair = 0,
+           cap_bvh = 0, cap_leaf = 0, cap_always = 0;
     // work buffers (grown on demand)
     double* scratch = nullptr; size_t scratch_cap = 0;  // doubles
     uint8_t* rgba = nullptr; size_t rgba_cap = 0;       // bytes
@@ -121,6 +125,10 @@ struct Device {
     unsigned* wf_free = nullptr; size_t wf_free_cap = 0;
     WfCounters* wf_cnt = nullptr; size_t wf_cnt_cap = 0;
     unsigned* wf_host = nullptr;  // pinned: n_in read back every few bounces
+    // tray_present work buffers, kept between calls
+    double4* pr_tmp = nullptr; size_t pr_tmp_cap = 0;
+    uchar4* pr_small = nullptr; size_t pr_small_cap = 0;
+    unsigned char* pr_ansi = nullptr; size_t pr_ansi_cap = 0;
     // PNG encoder work buffers (tray_encode_png), kept between calls
     unsigned char* png_filt = nullptr; size_t png_filt_cap = 0;
     unsigned char* png_out = nullptr; size_t png_out_cap = 0;
@@ -193,7 +201,8 @@ void free_scene(Device& d) {
     cudaFree(d.geo_d); cudaFree(d.geo_f); cudaFree(d.radius_d); cudaFree(d.radius_f); cudaFree(d.kind); cudaFree(d.params);
     cudaFree(d.fpair); d.fpair = nullptr;
     cudaFree(d.bvh); cudaFree(d.bvh_leaf_ids); cudaFree(d.bvh_always);
-    d.bvh = nullptr; d.bvh_leaf_ids = nullptr; d.bvh_always = nullptr; d.bvh_n_always = 0;
+    d.bvh = nullptr; d.bvh_leaf_ids = nullptr; d.bvh_always = nullptr; d.bvh_n_always = 0; d.bvh_present = false;
+    d.cap_geo_d = d.cap_geo_f = d.cap_radius_d = d.cap_radius_f = d.cap_kind = d.cap_params = d.cap_fpair = d.cap_bvh = d.cap_leaf = d.cap_always = 0;
     d.geo_d = nullptr; d.geo_f = nullptr; d.radius_d = nullptr; d.radius_f = nullptr; d.kind = nullptr; d.params = nullptr;
 }
 
@@ -202,7 +211,7 @@ template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device
     DevScene<double> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
-    s.bvh = d.bvh; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
+    s.bvh = d.bvh_present ? d.bvh : nullptr; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
@@ -482,8 +491,8 @@ bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<in
     L.keys = d.lbvh_keys;
     L.ids = d_int; L.parent = d_int + m; L.visits = d_int + 3 * m; L.depth = d_int + 4 * m;
     L.range = d.lbvh_int2; L.child = d.lbvh_int2 + m;
-    CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * (size_t)(2 * m - 1)));
-    CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * m));
+    grow(d.bvh, d.cap_bvh, (size_t)(2 * m - 1));
+    grow(d.bvh_leaf_ids, d.cap_leaf, (size_t)m);
     L.nodes = d.bvh; L.leaf_ids = d.bvh_leaf_ids;
     const int T = 256;
     lbvh_keys_kernel<<<(n_keys + T - 1) / T, T, 0, d.stream>>>(L);
@@ -495,11 +504,8 @@ bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<in
     int root_depth = 0;
     CK(cudaMemcpyAsync(&root_depth, L.depth, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
-    if (root_depth < 1 || root_depth > 40) {
-        cudaFree(d.bvh); cudaFree(d.bvh_leaf_ids);
-        d.bvh = nullptr; d.bvh_leaf_ids = nullptr;
-        return false;
-    }
+    if (root_depth < 1 || root_depth > 40) return false;
+    d.bvh_present = true;
     return true;
 }
 
@@ -583,6 +589,7 @@ void tray_destroy(tray_ctx* ctx) {
         cudaFree(d.lbvh_keys); cudaFree(d.lbvh_int); cudaFree(d.lbvh_int2);
         cudaFree(d.wf_rec); cudaFree(d.wf_queue); cudaFree(d.wf_free); cudaFree(d.wf_cnt);
         if (d.wf_host) cudaFreeHost(d.wf_host);
+        cudaFree(d.pr_tmp); cudaFree(d.pr_small); cudaFree(d.pr_ansi);
         cudaFree(d.png_filt); cudaFree(d.png_out); cudaFree(d.png_hist); cudaFree(d.png_piece); cudaFree(d.png_adler); cudaFree(d.png_blocks); cudaFree(d.png_tot); cudaFree(d.stats); cudaFree(d.srgb_thr);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -657,19 +664,19 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
-            free_scene(d);
+            d.bvh_present = false;
             d.n = n; d.n_pad = n_pad;
             d.filt_mc = mc; d.filt_r2max = r2max;
             d.bvh_n_always = (int)hb.always.size(); d.bvh_extent = hb.extent;
             if (!hb.always.empty()) {
-                CK(cudaMalloc(&d.bvh_always, sizeof(int) * hb.always.size()));
+                grow(d.bvh_always, d.cap_always, hb.always.size());
                 CK(cudaMemcpy(d.bvh_always, hb.always.data(), sizeof(int) * hb.always.size(), cudaMemcpyHostToDevice));
             }
-            CK(cudaMalloc(&d.fpair, sizeof(float4) * n_pad));
+            grow(d.fpair, d.cap_fpair, (size_t)n_pad);
             CK(cudaMemcpy(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMalloc(&d.geo_d, sizeof(double4) * n_pad)); CK(cudaMalloc(&d.geo_f, sizeof(float4) * n_pad));
-            CK(cudaMalloc(&d.radius_d, sizeof(double) * n_pad)); CK(cudaMalloc(&d.radius_f, sizeof(float) * n_pad));
-            CK(cudaMalloc(&d.kind, n_pad)); CK(cudaMalloc(&d.params, sizeof(double4) * n_pad));
+            grow(d.geo_d, d.cap_geo_d, (size_t)n_pad); grow(d.geo_f, d.cap_geo_f, (size_t)n_pad);
+            grow(d.radius_d, d.cap_radius_d, (size_t)n_pad); grow(d.radius_f, d.cap_radius_f, (size_t)n_pad);
+            grow(d.kind, d.cap_kind, (size_t)n_pad); grow(d.params, d.cap_params, (size_t)n_pad);
             CK(cudaMemcpy(d.geo_d, gd.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(d.geo_f, gf.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(d.radius_d, rd.data(), sizeof(double) * n_pad, cudaMemcpyHostToDevice));
@@ -682,9 +689,10 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             else {
                 if (!host_built) { std::vector<int> tmp = tree_ids; bvh_build_host(sc, hb, tmp); host_built = true; }
                 if (!hb.nodes.empty()) {
-                    CK(cudaMalloc(&d.bvh, sizeof(BvhNode) * hb.nodes.size()));
+                    grow(d.bvh, d.cap_bvh, hb.nodes.size());
                     CK(cudaMemcpy(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
-                    CK(cudaMalloc(&d.bvh_leaf_ids, sizeof(int) * hb.leaf_ids.size()));
+                    grow(d.bvh_leaf_ids, d.cap_leaf, hb.leaf_ids.size());
+                    d.bvh_present = true;
                     CK(cudaMemcpy(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice));
                 }
             }
@@ -1115,10 +1123,10 @@ int tray_present(tray_ctx* ctx, int32_t cols, int32_t rows2, uint8_t* rgba_small
     try {
         CK(cudaSetDevice(d.dev));
         const int sw = ctx->width, sh = ctx->height;
-        double4* tmp; uchar4* small; unsigned char* ansi;
-        CK(cudaMalloc(&tmp, sizeof(double4) * (size_t)cols * sh));
-        CK(cudaMalloc(&small, sizeof(uchar4) * (size_t)cols * rows2));
-        CK(cudaMalloc(&ansi, need));
+        grow(d.pr_tmp, d.pr_tmp_cap, (size_t)cols * sh);
+        grow(d.pr_small, d.pr_small_cap, (size_t)cols * rows2);
+        grow(d.pr_ansi, d.pr_ansi_cap, need);
+        double4* tmp = d.pr_tmp; uchar4* small = d.pr_small; unsigned char* ansi = d.pr_ansi;
         cudaEvent_t a = next_event(d), b = next_event(d);
         CK(cudaEventRecord(a, d.stream));
         if (sw < cols) {  // supersample < 1: the frame is smaller than the terminal -> draw.NearestNeighbor (main.go:124-125)
@@ -1136,7 +1144,6 @@ int tray_present(tray_ctx* ctx, int32_t cols, int32_t rows2, uint8_t* rgba_small
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, a, b));
         if (device_ms) *device_ms = ms;
-        cudaFree(tmp); cudaFree(small); cudaFree(ansi);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
 }
