@@ -340,8 +340,8 @@ def run_ours(args):
                          "note": notes[name]})
         # same default arithmetic, other divergence layout / closest-hit structure (results bit-identical)
         for name, setp, note in (
-                ("fp64, plain layout", lambda q: setattr(q, "layout", ray.LAYOUT_PLAIN),
-                 "default kernel without the per-material regrouping of paths inside the CTA (TRAY_LAYOUT_PLAIN)"),
+                ("fp64, regroup layout", lambda q: setattr(q, "layout", ray.LAYOUT_REGROUP),
+                 "default kernel plus per-material regrouping of the CTA's paths through shared memory after every Scene.Hit (TRAY_LAYOUT_REGROUP)"),
                 ("fp64, wavefront layout", lambda q: setattr(q, "layout", ray.LAYOUT_WAVEFRONT),
                  "path state in HBM, one bounce = intersect | shade over per-material queues | regenerate kernels (TRAY_LAYOUT_WAVEFRONT)"),
                 ("fp64, bvh", lambda q: setattr(q, "accel", ray.ACCEL_BVH),

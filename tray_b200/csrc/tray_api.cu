@@ -115,6 +115,7 @@ struct Device {
     double* hdr = nullptr; size_t hdr_cap = 0;          // doubles
     unsigned long long* counters = nullptr; int counters_cap = 0;
     unsigned short* stk_g = nullptr; size_t stk_cap = 0;  // regroup layout: attenuation stacks [level][slot]
+    CamRay* gen = nullptr; size_t gen_cap = 0;             // camera rays of a pass (camera_ray_kernel)
     // LBVH build scratch (tray_lbvh.cuh), kept between uploads
     unsigned long long* lbvh_keys = nullptr; size_t lbvh_keys_cap = 0;
     int* lbvh_int = nullptr; size_t lbvh_int_cap = 0;
@@ -363,23 +364,27 @@ int launch_trace_wavefront(Device& d, const TraceArgs& A, const DevScene<double>
 }
 
 #ifndef TRAY_DEFAULT_LAYOUT
-#define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_REGROUP  // measured: 103.1 ms vs 107.9 ms plain on config 2 (profiles/r01_*)
+#define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_PLAIN  // config 2, with the camera rays generated ahead: plain 99.7 ms, regroup 101.8, wavefront 120.9
 #endif
+// The wavefront layout exists for the strict fp64 linear scan only; everything else runs the megakernel.
+bool wavefront_runs(const Device& d, int precision, int accel, int layout) {
+    const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
+    const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
+    return layout == TRAY_LAYOUT_WAVEFRONT && precision == TRAY_FP64_STRICT && !bvh && (size_t)d.n_pad * 16 + tail <= kSmemBudget;
+}
+
 int launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precision, int accel, int layout) {
     const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
-    if (layout == TRAY_LAYOUT_AUTO) layout = TRAY_DEFAULT_LAYOUT;
-    if (layout == TRAY_LAYOUT_WAVEFRONT) {
-        const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
-        if (precision == TRAY_FP64_STRICT && !bvh && (size_t)d.n_pad * 16 + tail <= kSmemBudget)
-            return launch_trace_wavefront(d, A, dev_scene<double>(ctx, d));
-        layout = TRAY_LAYOUT_REGROUP;
-    }
+    const bool auto_layout = layout == TRAY_LAYOUT_AUTO;
+    if (auto_layout) layout = TRAY_DEFAULT_LAYOUT;
+    if (wavefront_runs(d, precision, accel, layout)) return launch_trace_wavefront(d, A, dev_scene<double>(ctx, d));
+    if (layout == TRAY_LAYOUT_WAVEFRONT) layout = TRAY_LAYOUT_REGROUP;
     const bool regroup = layout == TRAY_LAYOUT_REGROUP;
     if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh, regroup);
     else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
     // fp32 fast path: the same conservative pre-filter (it proves a miss in exact arithmetic), survivors tested in fp32
-    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, false, regroup);
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, false, regroup || auto_layout);  // fp32: regroup measures faster
     return 1;
 }
 
@@ -585,7 +590,7 @@ void tray_destroy(tray_ctx* ctx) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         free_scene(d);
-        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g);
+        cudaFree(d.scratch); cudaFree(d.rgba); cudaFree(d.hdr); cudaFree(d.counters); cudaFree(d.stk_g); cudaFree(d.gen);
         cudaFree(d.lbvh_keys); cudaFree(d.lbvh_int); cudaFree(d.lbvh_int2);
         cudaFree(d.wf_rec); cudaFree(d.wf_queue); cudaFree(d.wf_free); cudaFree(d.wf_cnt);
         if (d.wf_host) cudaFreeHost(d.wf_host);
@@ -875,7 +880,15 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.band_rows = kBandRows; A.shard_count = shard_count; A.shard_index = shard_index;
                     A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
-                    A.stk_g = nullptr; A.n_slots = 0;
+                    A.stk_g = nullptr; A.n_slots = 0; A.gen = nullptr;
+                    const bool wavefront = wavefront_runs(d, p->precision, p->accel, p->layout);  // generates its rays in wf_regen
+                    if (!wavefront) {
+                        grow(d.gen, d.gen_cap, (size_t)A.n_samples);
+                        camera_ray_kernel<<<(unsigned)((A.n_samples + 255) / 256), 256, 0, d.stream>>>(A, d.gen);
+                        CK(cudaGetLastError());
+                        A.gen = d.gen;
+                        launches++;
+                    }
                     CK(cudaEventRecord(next_event(d), d.stream));
                     launches += launch_trace(ctx, d, A, p->precision, p->accel, p->layout) - 1;
                     CK(cudaEventRecord(next_event(d), d.stream));

@@ -39,7 +39,44 @@ struct TraceArgs {
     unsigned long long* progress;    // samples finished (for tray_progress), may be null
     unsigned short* stk_g;           // regroup layout: attenuation stacks, [level][slot] (slot = launch-wide lane id)
     unsigned n_slots;
+    const struct CamRay* gen;        // camera rays of the pass, made by camera_ray_kernel
 };
+
+// One generated camera ray: what Tracer.RenderLines + Camera.GetRay leave behind for a sample (ray/tracer.go:133-141,
+// ray/camera.go:113-142): origin, direction and the generator state after the pixel-jitter and aperture draws.
+struct __align__(16) CamRay {
+    double o[3], d[3];
+    unsigned long long rng_hi, rng_lo;
+};
+
+// local sample of the pass -> pixel, sample number, stream; InDisc(RayRadius) iff NumRaysPerPixel > 1; GetRay
+__device__ __forceinline__ void camera_sample(const TraceArgs& A, unsigned my_li, Pcg& rng, V3<double>& o64, V3<double>& d64) {
+    unsigned lp = (unsigned)A.pass_pixel0 + my_li / (unsigned)A.spp_local;
+    int j = (int)(my_li % (unsigned)A.spp_local);
+    int s = A.sample_offset + j * A.sample_stride;
+    int ly = (int)(lp / (unsigned)A.width);
+    int x = (int)(lp - (unsigned)ly * (unsigned)A.width);
+    int y = A.shard_count <= 1 ? A.row0 + ly
+                               : A.row0 + ((ly / A.band_rows) * A.shard_count + A.shard_index) * A.band_rows + (ly - (ly / A.band_rows) * A.band_rows);
+    unsigned long long idx = ((unsigned long long)y * (unsigned)A.width + (unsigned)x) * (unsigned)A.spp + (unsigned)s;
+    rng = pcg_new_idx(idx, A.seed);
+    double jx = 0.0, jy = 0.0;
+    if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);  // ray/tracer.go:136-139
+    get_ray(A.cam, rng, (double)x, (double)y, jx, jy, o64, d64);
+}
+
+// All camera rays of a pass, one sample per thread with every lane busy: inside the megakernel the same code ran for the
+// few lanes of a warp whose path had just ended. 64 bytes per sample written here and read back once by trace_kernel.
+__global__ void __launch_bounds__(256) camera_ray_kernel(const __grid_constant__ TraceArgs A, CamRay* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_samples) return;
+    Pcg rng;
+    V3<double> o64, d64;
+    camera_sample(A, (unsigned)i, rng, o64, d64);
+    double2* q = reinterpret_cast<double2*>(out + i);
+    q[0] = make_double2(o64.x, o64.y); q[1] = make_double2(o64.z, d64.x); q[2] = make_double2(d64.y, d64.z);
+    reinterpret_cast<ulonglong2*>(q)[3] = make_ulonglong2(rng.hi, rng.lo);
+}
 
 __device__ __forceinline__ int map_row(const TraceArgs& A, int ly) {
     if (A.shard_count <= 1) return A.row0 + ly;
@@ -337,19 +374,12 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                 unsigned rank = __popc(need & lt_mask);
                 if (!has && rank < avail) {
                     my_li = pool_next + rank;
-                    // local sample -> pixel, sample number, global stream index
-                    unsigned lp = (unsigned)A.pass_pixel0 + my_li / (unsigned)A.spp_local;
-                    int j = (int)(my_li % (unsigned)A.spp_local);
-                    int s = A.sample_offset + j * A.sample_stride;
-                    int ly = (int)(lp / (unsigned)A.width);
-                    int x = (int)(lp - (unsigned)ly * (unsigned)A.width);
-                    int y = map_row(A, ly);
-                    unsigned long long idx = ((unsigned long long)y * (unsigned)A.width + (unsigned)x) * (unsigned)A.spp + (unsigned)s;
-                    rng = pcg_new_idx(idx, A.seed);
-                    double jx = 0.0, jy = 0.0;
-                    if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);  // ray/tracer.go:136-139
-                    V3<double> o64, d64;
-                    get_ray(A.cam, rng, (double)x, (double)y, jx, jy, o64, d64);
+                    // the camera ray and the generator state after its draws were made ahead by camera_ray_kernel
+                    const double2* q = reinterpret_cast<const double2*>(A.gen + my_li);
+                    const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+                    const ulonglong2 q3 = reinterpret_cast<const ulonglong2*>(q)[3];
+                    const V3<double> o64 = mk<double>(q0.x, q0.y, q1.x), d64 = mk<double>(q1.y, q2.x, q2.y);
+                    rng.hi = q3.x; rng.lo = q3.y;
                     O = mk<T>(T(o64.x), T(o64.y), T(o64.z));
                     D = mk<T>(T(d64.x), T(d64.y), T(d64.z));
                     depth_left = A.max_depth;
