@@ -191,8 +191,11 @@ func (t *Tracer) renderCUDA(scene *Scene, y0, y1, idx int) error {
 		p.sample_offset, p.sample_stride, p.sample_count = C.int32_t(cudaSubset.offset), C.int32_t(cudaSubset.stride), C.int32_t(cudaSubset.count)
 		p.sums_mode = cudaSubset.mode
 	}
-	if os.Getenv("TRAY_LAYOUT") == "plain" { // default: per-material regrouping inside the CTA (same results)
-		p.layout = C.TRAY_LAYOUT_PLAIN
+	switch os.Getenv("TRAY_LAYOUT") { // default: plain megakernel; the other layouts give the same bits
+	case "regroup":
+		p.layout = C.TRAY_LAYOUT_REGROUP
+	case "wavefront":
+		p.layout = C.TRAY_LAYOUT_WAVEFRONT
 	}
 	// ProgressFunc: poll the library from a goroutine; deltas sum to the pixel count (tracer_test.go:172-186).
 	done := make(chan struct{})
