@@ -298,7 +298,7 @@ def run_ours(args):
         if split_samples:
             xms = exchange()
             dev_ms += xms; exchange_ms += xms; launches += 1
-        segments += st["segments"]; paths += st["paths"]; trace_launches += st["launches"] // 2; sphere_tests += st["sphere_tests"]
+        segments += st["segments"]; paths += st["paths"]; trace_launches += int(st["trace_launches"]); sphere_tests += st["sphere_tests"]
     sync_all()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()

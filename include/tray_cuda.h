@@ -149,7 +149,8 @@ typedef struct {
     int32_t launches;      /* kernels launched by this call */
     int32_t n_devices;
     double trace_kernel_ms; /* device time of the trace kernels alone */
-    double reserved[3];
+    double trace_launches;  /* how many trace-kernel launches that was (one per pass and device; wavefront: one per bounce stage) */
+    double reserved[2];
 } tray_stats;
 
 /* Creates a context on the given CUDA devices (devices==NULL or n_devices<=0: device 0). */

@@ -39,7 +39,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu\n", offsetof(tray_params, seed), offsetof(tray_params, stream_idx), offsetof(tray_params, precision),
          offsetof(tray_params, shard_index), offsetof(tray_scene_desc, bg_a));
   printf("%zu %zu\n", offsetof(tray_params, sample_offset), offsetof(tray_params, sums_mode));
-  printf("%zu %zu\n", offsetof(tray_stats, kernel_ms), offsetof(tray_stats, trace_kernel_ms));
+  printf("%zu %zu %zu\n", offsetof(tray_stats, kernel_ms), offsetof(tray_stats, trace_kernel_ms), offsetof(tray_stats, trace_launches));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "a.c")
@@ -52,7 +52,7 @@ int main(void) {
     want = [ctypes.sizeof(S), ctypes.sizeof(_lib.CameraC), ctypes.sizeof(P), ctypes.sizeof(St),
             P.seed.offset, P.stream_idx.offset, P.precision.offset, P.shard_index.offset, S.bg_a.offset,
             P.sample_offset.offset, P.sums_mode.offset,
-            St.kernel_ms.offset, St.trace_kernel_ms.offset]
+            St.kernel_ms.offset, St.trace_kernel_ms.offset, St.trace_launches.offset]
     assert got == want
 
 

@@ -764,7 +764,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     const bool subset = p->sums_mode != TRAY_SUMS_OFF;
     const int rows = p->y1 - p->y0;
     const int G = (int)ctx->devs.size();
-    int launches = 0;
+    int launches = 0, trace_launch_count = 0;
     try {
         ctx->width = p->width; ctx->height = p->height; ctx->y0 = p->y0; ctx->y1 = p->y1;
         ctx->have_image = false; ctx->have_hdr = false;
@@ -812,6 +812,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                 CK(cudaGetLastError());
                 CK(cudaEventRecord(next_event(d), d.stream));
                 launches++;
+                trace_launch_count++;
             }
             CK(cudaEventRecord(d.ev_end, d.stream));
             for (int r = 0; r < rows; r++) d.local_rows.push_back(p->y0 + r);
@@ -890,7 +891,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                         launches++;
                     }
                     CK(cudaEventRecord(next_event(d), d.stream));
-                    launches += launch_trace(ctx, d, A, p->precision, p->accel, p->layout) - 1;
+                    const int n_tr = launch_trace(ctx, d, A, p->precision, p->accel, p->layout);
+                    launches += n_tr - 1;
+                    trace_launch_count += n_tr;
                     CK(cudaEventRecord(next_event(d), d.stream));
                     ResolveArgs R;
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
@@ -966,6 +969,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             stats->depth_exhausted = exh;
             stats->kernel_ms = kernel_ms;
             stats->trace_kernel_ms = trace_ms;
+            stats->trace_launches = (double)trace_launch_count;
             stats->launches = launches;
             stats->n_devices = G;
             stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
