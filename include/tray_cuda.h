@@ -16,6 +16,8 @@
  *   tray_camera        <- Camera after Initialize  ray/camera.go:9-39,43-105 (Initialize stays on the host)
  *   tray_first_hit     <- Scene.Hit + Sphere.Hit   ray/objects.go:37-46,81-104 (parity probe, RNG-free)
  *   tray_resolve_sums  <- the tail of RenderLines   ray/tracer.go:145-152 (colorSum * 1/N, ToSRGBA, Pix store)
+ *   tray_present       <- draw.BiLinear/NearestNeighbor.Scale + ap.ShowScaledImage   main.go:119-130 (tray's OnResize tail)
+ *   tray_configure     <- (no reference counterpart: where the closest-hit BVH of a large scene is built)
  *   tray_encode_png    <- SaveImage / png.Encode    main.go:26-36, benchmark/benchmark.go:23-33
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
  *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
