@@ -466,8 +466,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_used, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_used if peak_used else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per trace_kernel launch from %s (ncu --set full); algorithmic DRAM bytes per path: 64 B of "
-                                         "generated camera ray read + 24 B of sample colour written" % traffic_src if traffic else None,
+                         "traffic_note": "DRAM bytes per trace_kernel launch from %s (ncu --set full); algorithmic DRAM bytes per path: 24 B of "
+                                         "sample colour written (read back once by the resolve kernel)" % traffic_src if traffic else None,
                          "kernel": "tray::trace_kernel", "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(1, trace_launches),
                          "algorithmic_flops_per_launch": flops / max(1, trace_launches),
                          "flops_model": "18*sphere_tests + 155*segments (SURVEY 8d); sphere_tests = segments*N (N=%d) for the linear scan, "
@@ -484,7 +484,7 @@ def run_ours(args):
                                                     "ceiling of the pure FP64-pipe kernel (alt_modes: fp64-brute); results are bit-identical"}
                                            if args.precision == "fp64" and not uses_bvh else None),
                          "note": "achieved = algorithmic flops (SURVEY 8d: 18 per sphere test) / CUDA-event time of the trace kernel; compute-bound, HBM traffic "
-                                 "is ~90 B/path (camera ray in, sample colour out); tensor cores do not apply"},
+                                 "is ~30 B/path (sample colour out); tensor cores do not apply"},
             "segments_per_path": all_segments / all_paths,
         }
         if split_samples:

@@ -1,4 +1,4 @@
-"""Tuning aid: time the wavefront-layout variants in build/variants/ (TRAY_DEFAULT_LAYOUT=3 builds) on config 2."""
+"""Tuning aid: whole-frame time (all kernels) and image hash of every library variant in build/variants/ on config 2."""
 import glob, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
@@ -10,7 +10,9 @@ t = ray.New(1920, 1080); t.Camera = ray.RichSceneCamera(); t.MaxDepth, t.NumRays
 best = 1e9
 for rep in range(3):
     t.Render(scene); best = min(best, t.Stats["kernel_ms"])
-print(json.dumps(dict(ms=best, mpaths=t.Stats["paths"] / best / 1e3, launches=t.Stats["launches"])))
+import hashlib
+print(json.dumps(dict(ms=best, mpaths=t.Stats["paths"] / best / 1e3, launches=t.Stats["launches"], segments=t.Stats["segments"],
+                      image_sha=hashlib.sha1(t.imageData.tobytes()).hexdigest()[:12])))
 ''' % ROOT
 for lib in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so"))) + [os.path.join(ROOT, "tray_b200", "libtraycuda.so")]:
     r = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, TRAY_LIB=lib), capture_output=True, text=True)

@@ -253,7 +253,7 @@ void launch_trace_regroup(Device& d, TraceArgs A, const DevScene<T>& S, size_t s
 #define TRAY_FILTER_MINB 4
 #endif
     auto k = trace_kernel<T, FMA, kTPB, TRAY_FILTER_MINB, kGeoFilter, true>;
-    smem = ((smem + 15) & ~(size_t)15) + sizeof(RegroupBuf<kTPB>);
+    smem = ((smem + 15) & ~(size_t)15) + sizeof(RegroupBuf<kTPB>);  // (smem already holds the 16 bytes of alignment slack)
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, kTPB, smem));
@@ -288,7 +288,7 @@ template <typename T, bool FMA>
 struct TraceLaunch {
     static void run(Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, bool bvh = false, bool regroup = false) {
         typedef typename Vec4T<T>::type T4;
-        const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
+        const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t) + 16 + kGenPoolBytes<kTPB>;
         const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
         if constexpr (sizeof(T) == 8) {
             if (bvh) {
@@ -883,7 +883,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
                     A.stk_g = nullptr; A.n_slots = 0; A.gen = nullptr;
                     const bool wavefront = wavefront_runs(d, p->precision, p->accel, p->layout);  // generates its rays in wf_regen
-                    if (!wavefront) {
+                    if (!wavefront && !TRAY_GEN_INKERNEL) {
                         grow(d.gen, d.gen_cap, (size_t)A.n_samples);
                         camera_ray_kernel<<<(unsigned)((A.n_samples + 255) / 256), 256, 0, d.stream>>>(A, d.gen);
                         CK(cudaGetLastError());

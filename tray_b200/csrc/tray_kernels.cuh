@@ -42,6 +42,15 @@ struct TraceArgs {
     const struct CamRay* gen;        // camera rays of the pass, made by camera_ray_kernel
 };
 
+#ifndef TRAY_GEN_INKERNEL
+#define TRAY_GEN_INKERNEL 1
+#endif
+// TRAY_GEN_INKERNEL (default): every warp generates the camera rays of its next 32 samples itself -- all 32 lanes busy --
+// into a shared-memory pool, and regeneration takes them from there (measured 95.9 ms per config-2 frame). With 0 a separate
+// camera_ray_kernel makes all camera rays of the pass ahead and they travel through HBM, 64 B/path each way (97.8 ms).
+// Either way the per-sample camera code never runs on the handful of lanes whose path has just ended (101.2 ms).
+template <int TPB> constexpr size_t kGenPoolBytes = TRAY_GEN_INKERNEL ? (size_t)TPB * 64 : 0;
+
 // One generated camera ray: what Tracer.RenderLines + Camera.GetRay leave behind for a sample (ray/tracer.go:133-141,
 // ray/camera.go:113-142): origin, direction and the generator state after the pixel-jitter and aperture draws.
 struct __align__(16) CamRay {
@@ -330,7 +339,9 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     float4* sfp = reinterpret_cast<float4*>(smem_raw);  // kGeoFilter: n_pad/2 pairs x 2 float4
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
-    RegroupBuf<TPB>* xb = reinterpret_cast<RegroupBuf<TPB>*>(smem_raw + ((geo_bytes + sizeof(ZigTables) + (size_t)kCand * TPB * sizeof(uint16_t) + 15) & ~(size_t)15));
+    const size_t pool_off = (geo_bytes + sizeof(ZigTables) + (size_t)kCand * TPB * sizeof(uint16_t) + 15) & ~(size_t)15;
+    CamRay* gpool = reinterpret_cast<CamRay*>(smem_raw + pool_off) + (threadIdx.x & ~31);  // this warp's 32 generated camera rays
+    RegroupBuf<TPB>* xb = reinterpret_cast<RegroupBuf<TPB>*>(smem_raw + pool_off + kGenPoolBytes<TPB>);
     const int tid = threadIdx.x;
     if (GEO == kGeoShared)
         for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
@@ -345,6 +356,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     const unsigned lt_mask = (1u << lane) - 1u;
     bool has = false, exhausted = false;
     unsigned pool_next = 0, pool_end = 0, my_li = 0;  // local sample indices of this pass (< 2^32 by construction)
+    unsigned gen_first = 0, gen_avail = 0, gen_base = 0;  // TRAY_GEN_INKERNEL: generated rays waiting in this warp's pool
+    (void)gen_first; (void)gen_avail; (void)gen_base; (void)gpool;
     const unsigned n_samples = (unsigned)A.n_samples;
     // Idle lanes carry a ray that certainly misses everything (every sphere is far behind it), so the
     // hot loop needs no "has a path" test.
@@ -362,7 +375,11 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         if (!exhausted) {
             unsigned need = __ballot_sync(kFull, !has);
             while (need) {
+#if TRAY_GEN_INKERNEL
+                if (gen_avail == 0 && pool_next >= pool_end) {
+#else
                 if (pool_next >= pool_end) {
+#endif
                     unsigned long long base = 0;
                     if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)kBatch);
                     base = __shfl_sync(kFull, base, 0);
@@ -370,12 +387,34 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                     pool_next = (unsigned)base;
                     pool_end = (unsigned)base + kBatch < n_samples ? (unsigned)base + kBatch : n_samples;
                 }
+#if TRAY_GEN_INKERNEL
+                if (gen_avail == 0) {  // the whole warp generates the camera rays of the next (up to) 32 samples of its batch
+                    const unsigned n = pool_end - pool_next < 32u ? pool_end - pool_next : 32u;
+                    if ((unsigned)lane < n) {
+                        Pcg g;
+                        V3<double> o64, d64;
+                        camera_sample(A, pool_next + lane, g, o64, d64);
+                        double2* q = reinterpret_cast<double2*>(gpool + lane);
+                        q[0] = make_double2(o64.x, o64.y); q[1] = make_double2(o64.z, d64.x); q[2] = make_double2(d64.y, d64.z);
+                        reinterpret_cast<ulonglong2*>(q)[3] = make_ulonglong2(g.hi, g.lo);
+                    }
+                    __syncwarp();
+                    gen_first = 0; gen_avail = n; gen_base = pool_next;
+                    pool_next += n;
+                }
+                unsigned avail = gen_avail;
+                unsigned rank = __popc(need & lt_mask);
+                if (!has && rank < avail) {
+                    my_li = gen_base + gen_first + rank;
+                    const double2* q = reinterpret_cast<const double2*>(gpool + gen_first + rank);
+#else
                 unsigned avail = pool_end - pool_next;
                 unsigned rank = __popc(need & lt_mask);
                 if (!has && rank < avail) {
                     my_li = pool_next + rank;
                     // the camera ray and the generator state after its draws were made ahead by camera_ray_kernel
                     const double2* q = reinterpret_cast<const double2*>(A.gen + my_li);
+#endif
                     const double2 q0 = q[0], q1 = q[1], q2 = q[2];
                     const ulonglong2 q3 = reinterpret_cast<const ulonglong2*>(q)[3];
                     const V3<double> o64 = mk<double>(q0.x, q0.y, q1.x), d64 = mk<double>(q1.y, q2.x, q2.y);
@@ -387,7 +426,12 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                     has = true;
                 }
                 unsigned cnt = __popc(need);
+#if TRAY_GEN_INKERNEL
+                __syncwarp();
+                { unsigned took = cnt < avail ? cnt : avail; gen_first += took; gen_avail -= took; }
+#else
                 pool_next += cnt < avail ? cnt : avail;
+#endif
                 need = __ballot_sync(kFull, !has);
             }
         }
