@@ -158,8 +158,8 @@ def run_reference(args):
         return 0
     workload = args.workload or ("config2" if args.gpus == 1 else "config3")
     threads = host_threads()
-    total_budget = 150.0
-    per_step = max(2.0, min(25.0, total_budget / max(1, args.steps + args.warmup)))
+    total_budget = args.ref_budget
+    per_step = max(0.5, min(25.0, total_budget / max(1, args.steps + args.warmup)))
     cp = cpu_port_run(workload, threads, per_step)
     for _ in range(args.warmup):
         cpu_port_step(cp)
@@ -532,6 +532,7 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (bounded sample per step)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
     sys.stdout.flush()
