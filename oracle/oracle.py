@@ -220,6 +220,21 @@ def resolve_sums(sums, n_samples):
     return rgba
 
 
+VEC_OPS = {"Add": 0, "Sub": 1, "Mul": 2, "SMul": 3, "SDiv": 4, "Cross": 5, "Unit": 6, "Neg": 7, "Reflect": 8, "Refract": 9, "Minus": 10,
+           "Dot": 11, "Length": 12, "LengthSquared": 13, "NearZero": 14, "Surrounds": 15}
+
+
+def vec_op(name, u, v=None, w=None, t=0.0):
+    """The Vec3 helpers of ray/vec3.go as the oracle restates them; vector results as a 3-tuple, scalar ones as a float."""
+    op = VEC_OPS[name]
+    arr = lambda a: None if a is None else (C.c_double * 3)(*[float(x) for x in a])
+    out = (C.c_double * 4)()
+    lib().oracle_vec_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    if lib().oracle_vec_op(op, arr(u), arr(v), arr(w), float(t), out) != 0:
+        raise RuntimeError("oracle_vec_op failed")
+    return float(out[3]) if op >= 11 else (out[0], out[1], out[2])
+
+
 def first_hit(scene, cam, width, height, fma_mode=0):
     ids = np.zeros((height, width), dtype=np.int32)
     t = np.zeros((height, width))

@@ -644,6 +644,36 @@ EXPORT int oracle_resolve_sums(const double *sums, size_t n_pixels, uint64_t n_s
     return 0;
 }
 
+/* Probe of the Vec3 helpers the hot path is built from (ray/vec3.go:25-145), so that the reference's own tables
+ * (ray/vec3_test.go) can be replayed against this restatement. op: 0 Add 1 Sub 2 Mul 3 SMul(t) 4 SDiv(t) 5 Cross 6 Unit(u)
+ * 7 Neg(u) 8 Reflect(u,n=v) 9 Refract(u,n=v,eta=t) 10 Minus(u; v,w) = u-(v+w) (ray/vec3.go:44-55); scalar results in
+ * out[3]: 11 Dot 12 Length(u) 13 LengthSquared(u) 14 NearZero(u) 15 Interval{Start=u.x,End=u.y}.Surrounds(t). */
+EXPORT int oracle_vec_op(int op, const double *pu, const double *pv, const double *pw, double t, double *out4) {
+    v3 u = A3(pu), v = pv ? A3(pv) : V(0, 0, 0), w = pw ? A3(pw) : V(0, 0, 0), r = V(0, 0, 0);
+    double s = 0;
+    switch (op) {
+        case 0: r = v_add(u, v); break;
+        case 1: r = v_sub(u, v); break;
+        case 2: r = v_mul(u, v); break;
+        case 3: r = v_smul(u, t); break;
+        case 4: r = v_sdiv(u, t); break;
+        case 5: r = v_cross(u, v); break;
+        case 6: r = v_unit(u); break;
+        case 7: r = v_neg(u); break;
+        case 8: r = v_reflect(u, v); break;
+        case 9: r = v_refract(u, v, t); break;
+        case 10: r = v_sub(u, v_add(v, w)); break;
+        case 11: s = v_dot(u, v); break;
+        case 12: s = v_len(u); break;
+        case 13: s = v_len2(u); break;
+        case 14: s = v_near_zero(u); break;
+        case 15: s = (t > u.x && t < u.y) ? 1 : 0; break;  /* Interval.Surrounds, ray/vec3.go:198-200: exclusive */
+        default: return -1;
+    }
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = s;
+    return 0;
+}
+
 /* Tracer.RenderLines(idx, yStart, yEnd, scene) (ray/tracer.go:120): rows outside stay untouched. */
 EXPORT int oracle_render_lines(const oracle_scene *sc, const oracle_camera *cam, const oracle_params *p,
                                int idx, int y0, int y1, uint8_t *rgba, size_t stride, double *hdr, oracle_stats *stats) {
