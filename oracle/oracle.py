@@ -220,6 +220,17 @@ def resolve_sums(sums, n_samples):
     return rgba
 
 
+def get_rays(cam, calls, idx=0, seed=42):
+    """Camera.GetRay for consecutive calls [(px, py, ox, oy), ...] on one stream rand.NewIdx(idx, seed); returns (n, 6)."""
+    a = np.ascontiguousarray(calls, dtype=np.float64).reshape(-1, 4)
+    cols = [np.ascontiguousarray(a[:, k]) for k in range(4)]
+    out = np.zeros((len(a), 6))
+    lib().oracle_get_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p] * 5
+    if lib().oracle_get_rays(C.byref(cam), idx, seed, len(a), _p(cols[0]), _p(cols[1]), _p(cols[2]), _p(cols[3]), _p(out)) != 0:
+        raise RuntimeError("oracle_get_rays failed")
+    return out
+
+
 VEC_OPS = {"Add": 0, "Sub": 1, "Mul": 2, "SMul": 3, "SDiv": 4, "Cross": 5, "Unit": 6, "Neg": 7, "Reflect": 8, "Refract": 9, "Minus": 10,
            "Dot": 11, "Length": 12, "LengthSquared": 13, "NearZero": 14, "Surrounds": 15}
 

@@ -644,6 +644,20 @@ EXPORT int oracle_resolve_sums(const double *sums, size_t n_pixels, uint64_t n_s
     return 0;
 }
 
+/* Camera.GetRay (ray/camera.go:113-142) for n consecutive calls on ONE stream rand.NewIdx(idx, seed), like the reference's
+ * camera tests do with RandForTests() = rand.New(42) (camera_test.go:11-13). px/py/ox/oy: n values each; out: n x 6 (origin, dir). */
+EXPORT int oracle_get_rays(const oracle_camera *cam, uint64_t idx, uint64_t seed, int n, const double *px, const double *py,
+                           const double *ox, const double *oy, double *out) {
+    if (!cam || n < 0) return -1;
+    rng_t rng = rng_new_idx(idx, seed);
+    for (int k = 0; k < n; k++) {
+        ray_t r = get_ray(cam, &rng, px[k], py[k], ox[k], oy[k]);
+        out[6 * k] = r.o.x; out[6 * k + 1] = r.o.y; out[6 * k + 2] = r.o.z;
+        out[6 * k + 3] = r.d.x; out[6 * k + 4] = r.d.y; out[6 * k + 5] = r.d.z;
+    }
+    return 0;
+}
+
 /* Probe of the Vec3 helpers the hot path is built from (ray/vec3.go:25-145), so that the reference's own tables
  * (ray/vec3_test.go) can be replayed against this restatement. op: 0 Add 1 Sub 2 Mul 3 SMul(t) 4 SDiv(t) 5 Cross 6 Unit(u)
  * 7 Neg(u) 8 Reflect(u,n=v) 9 Refract(u,n=v,eta=t) 10 Minus(u; v,w) = u-(v+w) (ray/vec3.go:44-55); scalar results in

@@ -122,3 +122,32 @@ def test_sphere_hit_honours_the_exclusive_interval(O):      # the only Interval 
                                          ((1, 2, 3), (0, 1, 0), -1, (1, 1, 3)), ((2, 3, 4), (0.5, 0.25, 2), 2, (3, 3.5, 8))])
 def test_ray_at(O, o, d, t, want):                          # ray_test.go:20-58: At(t) = Origin + Direction*t
     assert O.vec_op("Add", o, O.vec_op("SMul", d, t=t)) == want
+
+
+# ---- Camera.GetRay (ray/camera_test.go:105-243) against the oracle's restatement ---------------------------------------
+def test_get_ray_pinhole_origin_is_the_position(O):         # camera_test.go:105-130
+    cam = O.camera_init(100, 100, position=(0, 0, 5), look_at=(0, 0, 0), aperture=0.0, focal_length=1.0)
+    r = O.get_rays(cam, [(50, 50, 0, 0), (50, 50, 0, 0), (25, 75, 0, 0)])
+    assert (r[:, :3] == [0, 0, 5]).all() and (r[0] == r[1]).all() and (r[0, 3:] != r[2, 3:]).any()
+
+
+def test_get_ray_depth_of_field_samples_the_lens(O):        # camera_test.go:132-162
+    cam = O.camera_init(100, 100, position=(0, 0, 5), look_at=(0, 0, 0), aperture=0.5, focal_length=1.0, focus_distance=5.0)
+    r = O.get_rays(cam, [(50, 50, 0, 0)] * 64)
+    d = ((r[:, :3] - [0, 0, 5]) ** 2).sum(axis=1) ** 0.5
+    assert (r[0, :3] != r[1, :3]).any() and (d <= 0.25).all() and d.max() > 0.05
+    # all rays of a pixel meet on the focus plane: origin + dir hits the same point (GetRay aims at pos + dir*focusTime)
+    focus = r[:, :3] + r[:, 3:]
+    assert abs(focus - focus[0]).max() < 1e-12
+
+
+def test_get_ray_offsets_move_the_direction_not_the_origin(O):   # camera_test.go:218-243
+    cam = O.camera_init(10, 10, position=(0, 0, 0), look_at=(0, 0, -1), vfov=90.0, focal_length=1.0)
+    r = O.get_rays(cam, [(5, 5, 0, 0), (5, 5, 0.3, 0.2)])
+    assert (r[0, :3] == r[1, :3]).all() and (r[0, 3:] != r[1, 3:]).any()
+
+
+def test_focus_distance_defaults_to_focal_length():         # camera_test.go:164-175 (host mirror: Initialize stays on the host)
+    c = ray.Camera(FocalLength=2.5)
+    c.Initialize(100, 100)
+    assert c.FocusDistance == c.FocalLength == 2.5
