@@ -42,6 +42,9 @@ struct TraceArgs {
     const struct CamRay* gen;        // camera rays of the pass, made by camera_ray_kernel
 };
 
+#ifndef TRAY_FILTER_PIPE
+#define TRAY_FILTER_PIPE 1  // 1: half-chunk double buffer (8 float4 in flight, 128 registers); 0: pair-by-pair (for 96-register builds)
+#endif
 #ifndef TRAY_GEN_INKERNEL
 #define TRAY_GEN_INKERNEL 1
 #endif
@@ -287,6 +290,7 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
         mask = __funnelshift_l((unsigned)my, mask, 1);
     };
     unsigned saddr = (unsigned)__cvta_generic_to_shared(sfp);
+#if TRAY_FILTER_PIPE
     float4 a0, a1, a2, a3, b0, b1, b2, b3;
     lds4(a0, saddr); lds4(a1, saddr + 16); lds4(a2, saddr + 32); lds4(a3, saddr + 48);
 #pragma unroll 1
@@ -296,6 +300,22 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
         pair(a0, a1); pair(a2, a3);
         lds4(a0, saddr + 128); lds4(a1, saddr + 144); lds4(a2, saddr + 160); lds4(a3, saddr + 176);
         pair(b0, b1); pair(b2, b3);
+#else
+    // low-register form (more resident warps hide the LDS latency instead): one pair in flight ahead of the one evaluated
+    float4 a0, a1, b0, b1;
+    lds4(a0, saddr); lds4(a1, saddr + 16);
+#pragma unroll 1
+    for (int i = 0; i < n_pad; i += CH) {
+        mask = 0;
+        lds4(b0, saddr + 32); lds4(b1, saddr + 48);
+        pair(a0, a1);
+        lds4(a0, saddr + 64); lds4(a1, saddr + 80);
+        pair(b0, b1);
+        lds4(b0, saddr + 96); lds4(b1, saddr + 112);
+        pair(a0, a1);
+        lds4(a0, saddr + 128); lds4(a1, saddr + 144);
+        pair(b0, b1);
+#endif
         saddr += 128;
         mask = ~mask & 0xffu;  // 1 = must be tested exactly
         if (mask_prev) {
