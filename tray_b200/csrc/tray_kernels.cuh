@@ -45,6 +45,9 @@ struct TraceArgs {
 #ifndef TRAY_FILTER_PIPE
 #define TRAY_FILTER_PIPE 1  // 1: half-chunk double buffer (8 float4 in flight, 128 registers); 0: pair-by-pair (for 96-register builds)
 #endif
+#ifndef TRAY_PARK_STATE
+#define TRAY_PARK_STATE 1  // park the fp64 ray, generator and path counters in shared memory across the filter scan: no spills at 128 registers, 94.7 vs 95.8 ms
+#endif
 #ifndef TRAY_GEN_INKERNEL
 #define TRAY_GEN_INKERNEL 1
 #endif
@@ -239,7 +242,7 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* sfp, const typename Vec4T<T>::type* __restrict__ ggeo,
                                     uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a,
-                                    T& best_t, int& best, int& ncand, unsigned& mask_prev) {
+                                    T& best_t, int& best, int& ncand, unsigned& mask_prev, const volatile double* parked = nullptr) {
     constexpr int CH = TRAY_CH;
     const int n_pad = S.n_pad;
     // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction, 8 instructions per pair) ----
@@ -320,7 +323,13 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
         mask = ~mask & 0xffu;  // 1 = must be tested exactly
         if (mask_prev) {
             if (ncand > kCand - CH) {  // list about to overflow (rare): run the exact test on what is queued
-                push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                if (parked) {  // TRAY_PARK_STATE: the fp64 ray waits in shared memory during the scan
+                    const T px_ = T(parked[0]), py_ = T(parked[TPB]), pz_ = T(parked[2 * TPB]);
+                    const T qx_ = T(parked[3 * TPB]), qy_ = T(parked[4 * TPB]), qz_ = T(parked[5 * TPB]);
+                    push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, px_, py_, pz_, qx_, qy_, qz_, (qx_ * qx_ + qy_ * qy_) + qz_ * qz_, &best_t, &best);
+                } else {
+                    push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, 0u, 0, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+                }
             }
             unsigned m = mask_prev;
             do {  // append in index order: bit CH-1-u <-> sphere (i-CH)+u
@@ -464,14 +473,39 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         T best_t = t_inf<T>();
         int best = -1;
         if (warp_alive) {  // (regroup layout: warps left without a path near the end of a pass skip the scan)
-        const T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
-        const T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
+#if TRAY_PARK_STATE
+        // Park what the scan does not need (fp64 ray, generator, counters of the path) in shared memory, so that the loop's
+        // registers are not shared with ~20 registers of path state.
+        __shared__ double s_park[8][TPB];
+        __shared__ int s_parki[3][TPB];
+        volatile double* pk = &s_park[0][tid];
+        volatile int* pki = &s_parki[0][tid];
+        constexpr bool kPark = GEO == kGeoFilter && !REGROUP;
+        if constexpr (kPark) {
+            pk[0] = (double)O.x; pk[TPB] = (double)O.y; pk[2 * TPB] = (double)O.z;
+            pk[3 * TPB] = (double)D.x; pk[4 * TPB] = (double)D.y; pk[5 * TPB] = (double)D.z;
+            pk[6 * TPB] = __longlong_as_double((long long)rng.hi); pk[7 * TPB] = __longlong_as_double((long long)rng.lo);
+            pki[0] = depth_left; pki[TPB] = sp; pki[2 * TPB] = (int)my_li;
+        }
+#endif
+        T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
+        T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
         int ncand = 0;
         unsigned mask_prev = 0;
         if constexpr (GEO == kGeoBVH) {
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
             if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
         } else if constexpr (GEO == kGeoFilter) {
+#if TRAY_PARK_STATE
+            if constexpr (kPark) {
+                filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pk);
+                ox = T(pk[0]); oy = T(pk[TPB]); oz = T(pk[2 * TPB]); dx = T(pk[3 * TPB]); dy = T(pk[4 * TPB]); dz = T(pk[5 * TPB]);
+                a = (dx * dx + dy * dy) + dz * dz;
+                O = mk<T>(ox, oy, oz); D = mk<T>(dx, dy, dz);
+                rng.hi = (uint64_t)__double_as_longlong(pk[6 * TPB]); rng.lo = (uint64_t)__double_as_longlong(pk[7 * TPB]);
+                depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
+            } else
+#endif
             filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
         } else {
         // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
