@@ -188,3 +188,53 @@ def ray_color(spheres, bg_a, bg_b, rng, o, d, depth):
     if s is None:
         return (0.0, 0.0, 0.0)
     return mul(s[0], ray_color(spheres, bg_a, bg_b, rng, p, s[1], depth - 1))
+
+
+# ---- ray/camera.go:113-142, ray/tracer.go:85-155 ----------------------------------------------------------------------------
+def get_ray(cam, rng, px, py, ox, oy):
+    """Camera.GetRay on an initialised camera (fields of oracle.Camera / tray_camera)."""
+    pos = tuple(cam.position)
+    sample = add(add(tuple(cam.pixel00), smul(tuple(cam.pixel_x), px + ox)), smul(tuple(cam.pixel_y), py + oy))
+    d = sub(sample, pos)
+    if cam.aperture > 0:
+        dx, dy = rng.InDisc(1.0)
+        offset = add(smul(tuple(cam.defocus_u), dx), smul(tuple(cam.defocus_v), dy))
+        focus_time = cam.focus_distance / cam.focal_length
+        focus_point = add(pos, smul(d, focus_time))
+        o = add(pos, offset)
+        return o, sub(focus_point, o)
+    return pos, d
+
+
+def render_lines(spheres, bg_a, bg_b, cam, width, spp, max_depth, ray_radius, seed, idx, y0, y1, to_srgb, per_sample=False):
+    """Tracer.RenderLines (tracer.go:120-155): ONE stream rand.NewIdx(idx, seed) for the call (or, with per_sample, the
+    convention of the throughput mode: one stream per sample, idx = (y*W+x)*spp+s). Returns {(x, y): (r, g, b)} in 8 bits."""
+    rng = Rand(idx, seed)
+    div = 1.0 / float(spp)
+    out = {}
+    for y in range(y0, y1):
+        for x in range(width):
+            csum = (0.0, 0.0, 0.0)
+            for s in range(spp):
+                if per_sample:
+                    rng = Rand((y * width + x) * spp + s, seed)
+                ox = oy = 0.0
+                if spp > 1:
+                    ox, oy = rng.InDisc(ray_radius)
+                o, d = get_ray(cam, rng, float(x), float(y), ox, oy)
+                csum = add(csum, ray_color(spheres, bg_a, bg_b, rng, o, d, max_depth))
+            c = smul(csum, div)
+            out[(x, y)] = tuple(to_srgb(v) for v in c)
+    return out
+
+
+def render(spheres, bg_a, bg_b, cam, width, height, spp, max_depth, ray_radius, seed, num_workers, to_srgb):
+    """Tracer.Render's fan-out (tracer.go:85-116): one stream idx 0 for a single worker, else chunks of max(4, h/(4W)) rows
+    whose stream index is their first row."""
+    if num_workers == 1:
+        return render_lines(spheres, bg_a, bg_b, cam, width, spp, max_depth, ray_radius, seed, 0, 0, height, to_srgb)
+    chunk = max(4, height // (num_workers * 4))
+    out = {}
+    for y in range(0, height, chunk):
+        out.update(render_lines(spheres, bg_a, bg_b, cam, width, spp, max_depth, ray_radius, seed, y, y, min(y + chunk, height), to_srgb))
+    return out

@@ -69,3 +69,28 @@ def test_ray_color_paths_agree_bit_for_bit(O, which):
         assert got == tuple(want), k
         nonsky += pyref.scene_hit(spheres, o, d, 1e-6, math.inf) is not None
     assert nonsky > 20
+
+
+@pytest.mark.parametrize("workers,spp,aperture", [(1, 3, 0.1), (2, 2, 0.0), (3, 1, 0.1)])
+def test_render_fan_out_and_sample_loop_agree(O, workers, spp, aperture):
+    """Tracer.Render / RenderLines: stream per chunk, InDisc(RayRadius) iff spp > 1, aperture draw iff Aperture > 0, sum in
+    sample order, * (1/N), ToSRGBA -- the image of the pure-Python restatement equals the C oracle's, pixel for pixel."""
+    from oracle import pyref
+    w, h, depth, seed = 14, 11, 12, 5
+    flat = O.rich_scene(2)
+    rc = dict(O.RICH_CAMERA)
+    rc["aperture"] = aperture
+    cam = O.camera_init(w, h, **rc)
+    spheres = _spheres(flat)
+    bg = ((1.0, 1.0, 1.0), (0.4, 0.65, 1.0))
+    p = O.make_params(w, h, spp=spp, max_depth=depth, seed=seed, num_workers=workers, stream_mode=0)
+    want, _, _ = O.render(flat, cam, p)
+    got = pyref.render(spheres, bg[0], bg[1], cam, w, h, spp, depth, 0.5, seed, workers, O.linear_to_srgb)
+    for (x, y), rgb in got.items():
+        assert tuple(int(v) for v in want[y, x, :3]) == rgb, (x, y)
+    # the per-sample stream convention of the throughput mode
+    p1 = O.make_params(w, h, spp=spp, max_depth=depth, seed=seed, num_workers=1, stream_mode=1)
+    want1, _, _ = O.render(flat, cam, p1)
+    got1 = pyref.render_lines(spheres, bg[0], bg[1], cam, w, spp, depth, 0.5, seed, 0, 0, h, O.linear_to_srgb, per_sample=True)
+    for (x, y), rgb in got1.items():
+        assert tuple(int(v) for v in want1[y, x, :3]) == rgb, (x, y)
