@@ -19,6 +19,7 @@
  *   tray_present       <- draw.BiLinear/NearestNeighbor.Scale + ap.ShowScaledImage   main.go:119-130 (tray's OnResize tail)
  *   tray_configure     <- (no reference counterpart: where the closest-hit BVH of a large scene is built)
  *   tray_encode_png    <- SaveImage / png.Encode    main.go:26-36, benchmark/benchmark.go:23-33
+ *   tray_upload_frame  <- (no reference counterpart: an image the context did not render, for present / PNG / tests)
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
  *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
  */
@@ -193,6 +194,11 @@ TRAY_API int tray_read_hdr(tray_ctx *ctx, double *hdr_out);
  * The caller must have synchronised any stream of its own that wrote the sums. rgba_out may be NULL. */
 TRAY_API int tray_device_sums(tray_ctx *ctx, double **device_ptr, uint64_t *n_doubles);
 TRAY_API int tray_resolve_sums(tray_ctx *ctx, uint64_t n_samples, uint8_t *rgba_out, size_t stride);
+
+/* Places an arbitrary RGBA8 frame (row y at rgba + y*stride) on the context's first device as "the last rendered frame", so
+ * that tray_present / tray_encode_png / tray_read_image also serve images this context did not render (and so that the
+ * tests can feed the encoder adversarial content). */
+TRAY_API int tray_upload_frame(tray_ctx *ctx, const uint8_t *rgba, size_t stride, int32_t width, int32_t height);
 
 /* The interactive path after Render (main.go:119-130), on the device: scale the last rendered frame (which must be
  * complete and resident on one device) to cols x rows2 pixels with draw.BiLinear semantics (x/image/draw, draw.Over onto

@@ -125,3 +125,47 @@ def test_png_error_paths(ctx):
     ctx.render(t.to_c(), p, None)
     with pytest.raises(ray.TrayError):
         ctx.encode_png(32, 16)
+
+
+def _fib_image(w, h, n_sym):
+    """Mostly constant frame whose byte histogram follows Fibonacci counts for n_sym values: the Huffman tree of a block is
+    ~n_sym levels deep before the 15-bit limit is applied (the case tests/test_png_huffman_model.py checks on the CPU)."""
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    img[..., 3] = 255
+    flat = img[:, :, :3].reshape(-1)
+    fib, pos = [1, 1], 5
+    while len(fib) < n_sym:
+        fib.append(fib[-1] + fib[-2])
+    for k, cnt in enumerate(fib):
+        # isolated bytes (every 7th) so that the Sub/Up/Paeth residuals keep the value and its negative rare as well
+        for _ in range(min(cnt, 4000)):
+            if pos >= len(flat):
+                break
+            flat[pos] = 3 + 5 * k
+            pos += 7
+    return img
+
+
+@pytest.mark.parametrize("n_sym,w,h", [(22, 640, 64), (30, 1024, 128), (12, 64, 8)])
+def test_png_length_limited_codes_on_skewed_histograms(ctx, n_sym, w, h):
+    from PIL import Image
+    img = _fib_image(w, h, n_sym)
+    ctx.upload_frame(img)
+    data, _ = ctx.encode_png(w, h)
+    got, chunks, _, _ = parse_png(data)                     # zlib.decompress raises on an over-subscribed / incomplete code
+    assert np.array_equal(got, img[:, :, :3])
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")), img[:, :, :3])
+
+
+def test_png_of_uploaded_random_and_flat_frames(ctx):
+    rs = np.random.RandomState(3)
+    for img in (rs.randint(0, 256, (37, 53, 4)).astype(np.uint8), np.full((16, 16, 4), 200, dtype=np.uint8), np.zeros((5, 300, 4), dtype=np.uint8)):
+        img[..., 3] = 255
+        ctx.upload_frame(img)
+        h, w = img.shape[:2]
+        data, _ = ctx.encode_png(w, h)
+        got, _, _, _ = parse_png(data)
+        assert np.array_equal(got, img[:, :, :3])
+        back = np.zeros_like(img)
+        ctx.read_image(back)
+        assert np.array_equal(back, img)

@@ -990,6 +990,24 @@ int tray_read_image(tray_ctx* ctx, uint8_t* rgba_out, size_t stride) {
     return TRAY_OK;
 }
 
+int tray_upload_frame(tray_ctx* ctx, const uint8_t* rgba, size_t stride, int32_t width, int32_t height) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!rgba || width <= 0 || height <= 0 || stride < (size_t)width * 4) return fail(ctx, TRAY_E_INVALID, "tray_upload_frame: bad argument");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        const size_t row_bytes = (size_t)width * 4;
+        grow(d.rgba, d.rgba_cap, row_bytes * height);
+        CK(cudaMemcpy2D(d.rgba, row_bytes, rgba, stride, row_bytes, (size_t)height, cudaMemcpyHostToDevice));
+        for (Device& dv : ctx->devs) dv.local_rows.clear();
+        for (int y = 0; y < height; y++) d.local_rows.push_back(y);
+        ctx->width = width; ctx->height = height; ctx->y0 = 0; ctx->y1 = height;
+        ctx->have_image = true; ctx->have_hdr = false; ctx->hdr_is_sums = false;
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
 int tray_read_hdr(tray_ctx* ctx, double* hdr_out) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);

@@ -155,14 +155,11 @@ __device__ void png_code_lengths(const unsigned* freq, const short* order, int m
     int bl_count[32];
     for (int b = 0; b < 32; b++) bl_count[b] = 0;
     int overflow = 0;
-    for (int nd = 2 * m - 3; nd >= 0; nd--) {
+    for (int nd = 2 * m - 3; nd >= 0; nd--) {  // root downwards: interior nodes (m..2m-2) come before the leaves (0..m-1)
         int d = depth[parent[nd]] + 1;
-        if (d > 31) d = 31;
+        if (d > maxbits) { d = maxbits; overflow++; }  // as zlib's gen_bitlen: EVERY node below the limit counts, interior ones too
         depth[nd] = (unsigned char)d;
-        if (nd < m) {
-            if (d > maxbits) { d = maxbits; overflow++; }
-            bl_count[d]++;
-        }
+        if (nd < m) bl_count[d]++;
     }
     while (overflow > 0) {
         int bits = maxbits - 1;

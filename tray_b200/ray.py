@@ -313,6 +313,12 @@ class Context:
                                                      buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(ms)))
         return buf[:n.value].tobytes(), small, ms.value
 
+    def upload_frame(self, img):
+        """An arbitrary (h, w, 4) uint8 image becomes "the last rendered frame" (for present / encode_png / tests)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        _lib.check(self.handle, self._L.tray_upload_frame(self.handle, img.ctypes.data_as(C.c_void_p), img.strides[0], w, h))
+
     def encode_png(self, width, height):
         """SaveImage's png.Encode (main.go:26-36) on the device: returns (PNG file bytes, device ms)."""
         cap = int(self._L.tray_png_bound(width, height))
