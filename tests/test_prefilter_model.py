@@ -113,3 +113,52 @@ def test_filter_never_skips_a_sphere_the_strict_test_would_hit():
         else:
             kept += 1
     assert skipped > 2500 and hits > 2500 and kept > 2500      # the attack did reach both sides of the filter
+
+
+def test_fp64_sign_bit_rule_never_drops_a_hit():
+    """The all-fp64 loops (and the re-check in front of every exact test) call a sphere "certainly missed" from three sign
+    bits: disc < 0, or h < 0 with c >= 0 (miss_bits in tray_device.cuh, strict evaluation order of sphere_terms). Same attack
+    as above, in fp64: the reference's Sphere.Hit must return no hit whenever the rule fires -- tangent rays, origins on the
+    surface (c = +-0, tiny), h = -0 included."""
+    from oracle import pyref
+    rs = np.random.RandomState(12)
+    fired = hits = 0
+    for trial in range(30000):
+        scale = float(rs.choice([1.0, 12.0, 1000.0]))
+        r = float(rs.choice([0.2, 1.0, 1000.0, 0.01]))
+        c = tuple(float(v) for v in rs.uniform(-scale, scale, 3))
+        dirn = rs.normal(0, 1, 3)
+        dirn /= np.linalg.norm(dirn)
+        kind = trial % 4
+        if kind == 0:
+            perp = np.cross(dirn, rs.normal(0, 1, 3))
+            perp /= np.linalg.norm(perp)
+            eps = float(rs.choice([0.0, 1e-16, 1e-15, 1e-12, 1e-9, 1e-6])) * float(rs.choice([-1, 1]))
+            o = np.array(c) + perp * r * (1 + eps) - dirn * float(rs.uniform(0.0, 3.0) * r)
+        elif kind == 1:
+            n = rs.normal(0, 1, 3)
+            n /= np.linalg.norm(n)
+            o = np.array(c) + n * r
+            dirn = n * float(rs.choice([1, -1])) + rs.normal(0, 1, 3) * float(rs.choice([0.0, 1e-9, 0.5]))
+        elif kind == 2:
+            o = np.array(c) + dirn * r * float(rs.choice([-1.0, -1.0000001, -5.0, 1.0, 5.0]))
+            if rs.rand() < 0.5:
+                dirn = np.array([0.0, 0.0, 1.0]) if rs.rand() < 0.5 else dirn   # axis-parallel: exact zeros in h
+        else:
+            o = rs.uniform(-1.5, 1.5, 3) * scale
+        if not np.any(dirn):
+            continue
+        o = tuple(float(v) for v in o)
+        d = tuple(float(v) for v in dirn * float(rs.choice([1e-3, 1.0, 10.0])))
+        ocx, ocy, ocz = c[0] - o[0], c[1] - o[1], c[2] - o[2]
+        a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+        h = d[0] * ocx + d[1] * ocy + d[2] * ocz
+        cc = (ocx * ocx + ocy * ocy + ocz * ocz) - r * r
+        disc = h * h - a * cc
+        sb = lambda v: math.copysign(1.0, v) < 0                     # the sign BIT, as the kernel reads it
+        hit = pyref.sphere_hit(c, r, o, d, 1e-6, math.inf)
+        hits += hit is not None
+        if sb(disc) or (sb(h) and not sb(cc)):
+            fired += 1
+            assert hit is None, (trial, o, d, c, r, h, cc, disc)
+    assert fired > 5000 and hits > 5000
