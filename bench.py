@@ -344,6 +344,8 @@ def run_ours(args):
                  "default kernel plus per-material regrouping of the CTA's paths through shared memory after every Scene.Hit (TRAY_LAYOUT_REGROUP)"),
                 ("fp64, wavefront layout", lambda q: setattr(q, "layout", ray.LAYOUT_WAVEFRONT),
                  "path state in HBM, one bounce = intersect | shade over per-material queues | regenerate kernels (TRAY_LAYOUT_WAVEFRONT)"),
+                ("fp64, linear scan", lambda q: setattr(q, "accel", ray.ACCEL_BRUTE),
+                 "round-1 default: every sphere of the table through the exact fp32 pair pre-filter, reference order (TRAY_ACCEL_BRUTE)"),
                 ("fp64, bvh", lambda q: setattr(q, "accel", ray.ACCEL_BVH),
                  "small BVH instead of the linear scan (TRAY_ACCEL_BVH): far fewer sphere tests, so no roofline claim; image bit-identical")):
             p2 = tr._params(0, h)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAY_ABI_VERSION 2
+#define TRAY_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TRAY_API __attribute__((visibility("default")))
@@ -69,9 +69,11 @@ extern "C" {
 #define TRAY_FP64_STRICT_BRUTE 3 /* as STRICT but every test in fp64 (no pre-filter): the pure FP64-pipe kernel */
 
 /* closest-hit structure. Results are identical for all of them (ties resolve to the lowest index). */
-#define TRAY_ACCEL_AUTO 0  /* brute force up to 2048 spheres, BVH above */
+#define TRAY_ACCEL_AUTO 0  /* two-level clusters up to 2048 spheres, BVH above */
 #define TRAY_ACCEL_BRUTE 1 /* linear scan of the sphere table (the reference's Scene.Hit order) */
 #define TRAY_ACCEL_BVH 2   /* small BVH (<= 4 spheres per leaf), built at upload on the host (median split) or on the device (LBVH) */
+#define TRAY_ACCEL_CLUSTER 3 /* two-level boxes over chunks of 8 spheres, tested warp-wide with a conservative fp32 slab test; only the
+                                chunks some lane of the warp may hit run the pair pre-filter (strict fp64 / fp32 modes; <= 4096 spheres) */
 
 /* divergence layout of the trace kernel. Results are identical for all of them. */
 #define TRAY_LAYOUT_AUTO 0
@@ -145,7 +147,7 @@ typedef struct {
 typedef struct {
     uint64_t paths;        /* samples traced (w*rows*spp) */
     uint64_t segments;     /* Scene.Hit calls, primary included */
-    uint64_t sphere_tests; /* Sphere.Hit evaluations */
+    uint64_t sphere_tests; /* Sphere.Hit evaluations: segments*n for the linear scan; spheres of the scanned chunks (clusters); exact tests (BVH) */
     uint64_t depth_exhausted; /* paths that ran into MaxDepth */
     double kernel_ms;      /* device time of the trace+resolve kernels (CUDA events, max over devices) */
     double total_ms;       /* wall time inside tray_render, copies included */
@@ -153,7 +155,8 @@ typedef struct {
     int32_t n_devices;
     double trace_kernel_ms; /* device time of the trace kernels alone */
     double trace_launches;  /* how many trace-kernel launches that was (one per pass and device; wavefront: one per bounce stage) */
-    double reserved[2];
+    double box_tests;       /* TRAY_ACCEL_CLUSTER: conservative box tests evaluated (groups + chunks), summed over rays */
+    double reserved[1];
 } tray_stats;
 
 /* Creates a context on the given CUDA devices (devices==NULL or n_devices<=0: device 0). */

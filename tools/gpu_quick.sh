@@ -1,7 +1,7 @@
 #!/bin/bash
-# Quick GPU visit: parity tests, short bench, one full ncu capture of the trace kernel (+ per-line export happens on the CPU side).
+# Quick GPU visit: parity tests, short bench, optionally one full ncu capture of the trace kernel (per-line export happens on the CPU side).
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_quick.log
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -2 gpurun_out/bench_quick.err
 python - <<'PY'
 import json

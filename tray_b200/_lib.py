@@ -12,7 +12,7 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = 0, 1, 2
 STREAM_REFERENCE, STREAM_PER_SAMPLE = 0, 1
 FP64_FMA, FP64_STRICT, FP32, FP64_STRICT_BRUTE = 0, 1, 2, 3
 SPLIT_TILES, SPLIT_SAMPLES = 0, 1
-ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
+ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER = 0, 1, 2, 3
 SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
 LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, LAYOUT_WAVEFRONT = 0, 1, 2, 3
 CFG_BVH_BUILD, BVH_BUILD_AUTO, BVH_BUILD_HOST, BVH_BUILD_DEVICE = 1, 0, 1, 2
@@ -51,7 +51,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("depth_exhausted", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("launches", C.c_int32), ("n_devices", C.c_int32), ("trace_kernel_ms", C.c_double),
-                ("trace_launches", C.c_double), ("reserved", C.c_double * 2)]
+                ("trace_launches", C.c_double), ("box_tests", C.c_double), ("reserved", C.c_double * 1)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

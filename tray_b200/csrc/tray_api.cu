@@ -104,6 +104,10 @@ struct Device {
     double* radius_d = nullptr; float* radius_f = nullptr;
     uint8_t* kind = nullptr; double4* params = nullptr;
     float4* fpair = nullptr; float filt_mc = 0, filt_r2max = 0;
+    // two-level cluster tables (cluster_scan)
+    float4* cl_blob = nullptr; size_t cap_cl_blob = 0;
+    int cl_blob_f4 = 0, cl_off_box2 = 0, cl_off_box1 = 0, cl_off_ids = 0, cl_real_groups = 0, cl_always_groups = 0;
+    unsigned cl_always_last = 0; float cl_r = 0; bool cl_present = false;
     BvhNode* bvh = nullptr; int* bvh_leaf_ids = nullptr; int* bvh_always = nullptr; int bvh_n_always = 0; double bvh_extent = 0;
     bool bvh_present = false;
     // the scene buffers are kept between uploads and only grown (cudaFree / cudaMalloc per keypress cost up to tens of ms)
@@ -180,6 +184,7 @@ struct tray_ctx {
     int split_mode = 0;
     int bvh_build = TRAY_BVH_BUILD_AUTO;  // tray_configure(TRAY_CFG_BVH_BUILD)
     int bvh_built_on_device = 0;          // what the last upload did (tray_query)
+    int cluster_unfilterable = 0;         // spheres of the scene the fp32 filter cannot bound (every ray tests them exactly)
     bool hdr_is_sums = false;          // last render left raw colour sums (sums_mode != 0)
     uint64_t sums_samples = 0;         // samples per pixel accumulated in them
     int sums_key[6] = {0, 0, 0, 0, 0, 0};  // geometry the sums belong to (w, h, y0, y1, shard_index, shard_count)
@@ -201,17 +206,25 @@ void free_scene(Device& d) {
     cudaSetDevice(d.dev);
     cudaFree(d.geo_d); cudaFree(d.geo_f); cudaFree(d.radius_d); cudaFree(d.radius_f); cudaFree(d.kind); cudaFree(d.params);
     cudaFree(d.fpair); d.fpair = nullptr;
+    cudaFree(d.cl_blob); d.cl_blob = nullptr; d.cap_cl_blob = 0; d.cl_present = false;
     cudaFree(d.bvh); cudaFree(d.bvh_leaf_ids); cudaFree(d.bvh_always);
     d.bvh = nullptr; d.bvh_leaf_ids = nullptr; d.bvh_always = nullptr; d.bvh_n_always = 0; d.bvh_present = false;
     d.cap_geo_d = d.cap_geo_f = d.cap_radius_d = d.cap_radius_f = d.cap_kind = d.cap_params = d.cap_fpair = d.cap_bvh = d.cap_leaf = d.cap_always = 0;
     d.geo_d = nullptr; d.geo_f = nullptr; d.radius_d = nullptr; d.radius_f = nullptr; d.kind = nullptr; d.params = nullptr;
 }
 
+template <typename T>
+void fill_cluster(DevScene<T>& s, const Device& d) {
+    s.cl_blob = d.cl_present ? d.cl_blob : nullptr; s.cl_blob_f4 = d.cl_blob_f4;
+    s.cl_off_box2 = d.cl_off_box2; s.cl_off_box1 = d.cl_off_box1; s.cl_off_ids = d.cl_off_ids;
+    s.cl_real_groups = d.cl_real_groups; s.cl_always_groups = d.cl_always_groups; s.cl_always_last = d.cl_always_last; s.cl_r = d.cl_r;
+}
 template <typename T> DevScene<T> dev_scene(const tray_ctx* ctx, const Device& d);
 template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device& d) {
     DevScene<double> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
+    fill_cluster(s, d);
     s.bvh = d.bvh_present ? d.bvh : nullptr; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
@@ -220,6 +233,7 @@ template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& 
     DevScene<float> s;
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
+    fill_cluster(s, d);
     s.bvh = nullptr; s.bvh_leaf_ids = nullptr; s.bvh_always = nullptr; s.bvh_n_always = 0; s.bvh_extent = 0;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
@@ -247,12 +261,12 @@ constexpr size_t kSmemBudget = 200 * 1024;
 
 // Regroup layout (pre-filter kernel only): same launch shape, plus the exchange area in shared memory and the
 // attenuation stacks in global memory (max_depth x lanes x 2 bytes, L2 resident).
-template <typename T, bool FMA>
+template <typename T, bool FMA, int GEO>
 void launch_trace_regroup(Device& d, TraceArgs A, const DevScene<T>& S, size_t smem) {
 #ifndef TRAY_FILTER_MINB
 #define TRAY_FILTER_MINB 4
 #endif
-    auto k = trace_kernel<T, FMA, kTPB, TRAY_FILTER_MINB, kGeoFilter, true>;
+    auto k = trace_kernel<T, FMA, kTPB, TRAY_FILTER_MINB, GEO, true>;
     smem = ((smem + 15) & ~(size_t)15) + sizeof(RegroupBuf<kTPB>);  // (smem already holds the 16 bytes of alignment slack)
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -262,19 +276,22 @@ void launch_trace_regroup(Device& d, TraceArgs A, const DevScene<T>& S, size_t s
     A.n_slots = grid * kTPB;
     grow(d.stk_g, d.stk_cap, (size_t)A.n_slots * (size_t)A.max_depth);
     A.stk_g = d.stk_g;
-    GeoArg<T, kGeoFilter> none{};
+    GeoArg<T, GEO> none{};
     k<<<grid, kTPB, smem, d.stream>>>(A, S, none);
     CK(cudaGetLastError());
 }
 
 template <typename T, bool FMA, int GEO>
 void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S, const GeoArg<T, GEO>& GP, size_t smem) {
-    // register budget: the pre-filter kernel keeps both the fp32 filter state and the fp64 ray live: 128 regs x 16 warps/SM
+    // register budget: the pre-filter kernels keep both the fp32 filter state and the fp64 ray live: 128 regs x 16 warps/SM
     // measured best (140.8 vs 143.3 ms); the pure-fp64 kernels prefer 96 regs x 20 warps/SM (211.8 vs 216.7 ms).
 #ifndef TRAY_FILTER_MINB
 #define TRAY_FILTER_MINB 4
 #endif
-    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : kMinBlocks;
+#ifndef TRAY_CLUSTER_MINB
+#define TRAY_CLUSTER_MINB 4
+#endif
+    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : (GEO == kGeoCluster ? TRAY_CLUSTER_MINB : kMinBlocks);
     auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -284,21 +301,30 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
     CK(cudaGetLastError());
 }
 
+// which closest-hit structure a render uses (results are identical for all of them)
+enum { kUseLinear = 0, kUseBvh = 1, kUseCluster = 2 };
+
 template <typename T, bool FMA>
 struct TraceLaunch {
-    static void run(Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, bool bvh = false, bool regroup = false) {
+    static void run(Device& d, const TraceArgs& A, const DevScene<T>& S, const void* host_geo, bool filter = false, int use = kUseLinear, bool regroup = false) {
         typedef typename Vec4T<T>::type T4;
         const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t) + 16 + kGenPoolBytes<kTPB>;
         const size_t geo_bytes = (size_t)S.n_pad * sizeof(T4);
         if constexpr (sizeof(T) == 8) {
-            if (bvh) {
+            if (use == kUseBvh) {
                 GeoArg<T, kGeoBVH> none{};
                 launch_trace_geo<T, FMA, kGeoBVH>(d, A, S, none, tail);
                 return;
             }
         }
+        if (filter && use == kUseCluster && S.cl_blob && (size_t)S.cl_blob_f4 * 16 + tail <= kSmemBudget) {
+            if (regroup) { launch_trace_regroup<T, FMA, kGeoCluster>(d, A, S, (size_t)S.cl_blob_f4 * 16 + tail); return; }
+            GeoArg<T, kGeoCluster> none{};
+            launch_trace_geo<T, FMA, kGeoCluster>(d, A, S, none, (size_t)S.cl_blob_f4 * 16 + tail);
+            return;
+        }
         if (filter && S.fpair && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
-            if (regroup) { launch_trace_regroup<T, FMA>(d, A, S, (size_t)S.n_pad * 16 + tail); return; }
+            if (regroup) { launch_trace_regroup<T, FMA, kGeoFilter>(d, A, S, (size_t)S.n_pad * 16 + tail); return; }
             GeoArg<T, kGeoFilter> none{};
             launch_trace_geo<T, FMA, kGeoFilter>(d, A, S, none, (size_t)S.n_pad * 16 + tail);
             return;
@@ -366,25 +392,39 @@ int launch_trace_wavefront(Device& d, const TraceArgs& A, const DevScene<double>
 #ifndef TRAY_DEFAULT_LAYOUT
 #define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_PLAIN  // config 2, with the camera rays generated ahead: plain 99.7 ms, regroup 101.8, wavefront 120.9
 #endif
+// AUTO: two-level clusters while the scene is small enough for their tables (and the filter can bound nearly all of it),
+// the per-lane BVH above; BRUTE: the linear scan in the reference's Scene.Hit order.
+constexpr int kAutoClusterMax = 2048, kAutoClusterUnfilterable = 64;
+int closest_hit_structure(const tray_ctx* ctx, const Device& d, int accel) {
+    const bool cluster_ok = d.cl_present;
+    if (accel == TRAY_ACCEL_BVH) return kUseBvh;
+    if (accel == TRAY_ACCEL_CLUSTER) return cluster_ok ? kUseCluster : kUseLinear;
+    if (accel == TRAY_ACCEL_BRUTE) return kUseLinear;
+    if (cluster_ok && d.n <= kAutoClusterMax && ctx->cluster_unfilterable <= kAutoClusterUnfilterable) return kUseCluster;
+    return d.n > kAutoClusterMax ? kUseBvh : kUseLinear;
+}
+
 // The wavefront layout exists for the strict fp64 linear scan only; everything else runs the megakernel.
-bool wavefront_runs(const Device& d, int precision, int accel, int layout) {
-    const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
+bool wavefront_runs(const tray_ctx* ctx, const Device& d, int precision, int accel, int layout) {
+    const bool bvh = closest_hit_structure(ctx, d, accel) == kUseBvh;
     const size_t tail = sizeof(ZigTables) + (size_t)kCand * kTPB * sizeof(uint16_t);
     return layout == TRAY_LAYOUT_WAVEFRONT && precision == TRAY_FP64_STRICT && !bvh && (size_t)d.n_pad * 16 + tail <= kSmemBudget;
 }
 
 int launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precision, int accel, int layout) {
-    const bool bvh = accel == TRAY_ACCEL_BVH || (accel == TRAY_ACCEL_AUTO && d.n > 2048);
+    const int use = closest_hit_structure(ctx, d, accel);
     const bool auto_layout = layout == TRAY_LAYOUT_AUTO;
     if (auto_layout) layout = TRAY_DEFAULT_LAYOUT;
-    if (wavefront_runs(d, precision, accel, layout)) return launch_trace_wavefront(d, A, dev_scene<double>(ctx, d));
+    if (wavefront_runs(ctx, d, precision, accel, layout)) return launch_trace_wavefront(d, A, dev_scene<double>(ctx, d));
     if (layout == TRAY_LAYOUT_WAVEFRONT) layout = TRAY_LAYOUT_REGROUP;
     const bool regroup = layout == TRAY_LAYOUT_REGROUP;
-    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
-    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, bvh, regroup);
-    else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, bvh);
+    // the all-fp64 kernels (FMA, STRICT_BRUTE) scan linearly or walk the BVH; the pre-filter kernels add the cluster structure
+    const int use64 = use == kUseBvh ? kUseBvh : kUseLinear;
+    if (precision == TRAY_FP64_FMA) TraceLaunch<double, true>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, use64);
+    else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, use, regroup);
+    else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, use64);
     // fp32 fast path: the same conservative pre-filter (it proves a miss in exact arithmetic), survivors tested in fp32
-    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, false, regroup || auto_layout);  // fp32: regroup measures faster
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, use == kUseBvh ? kUseLinear : use, regroup || auto_layout);  // fp32: regroup measures faster
     return 1;
 }
 
@@ -514,6 +554,159 @@ bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<in
     return true;
 }
 
+// ---- two-level cluster tables for cluster_scan (tray_kernels.cuh) ------------------------------------------------
+// Spheres the pre-filter can bound are split recursively at the median of the longest centroid axis into groups of 64
+// and those into chunks of 8 (every part full except the last), so that chunk = 8 consecutive slots and group = 8
+// consecutive chunks are spatially compact. Spheres outside the filter's range (|C|inf > 256, r^2 > 256, non-finite) and,
+// when there are only a few, spheres much larger than the rest go into "always" groups that every ray scans.
+struct ClusterHost {
+    std::vector<float4> blob;
+    int off_box2 = 0, off_box1 = 0, off_ids = 0, real_groups = 0, always_groups = 0;
+    unsigned always_last = 0;
+    float r = 0;
+    int unfilterable = 0;
+};
+
+void cluster_split(const tray_scene_desc* sc, std::vector<int>& ids, int first, int n, int leaf, std::vector<std::pair<int, int>>& out) {
+    if (n <= leaf) { if (n > 0) out.push_back({first, n}); return; }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int j = 0; j < n; j++) {
+        const int i = ids[first + j];
+        const double c[3] = {sc->cx[i], sc->cy[i], sc->cz[i]};
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], c[k]); hi[k] = std::max(hi[k], c[k]); }
+    }
+    int axis = 0;
+    if (hi[1] - lo[1] > hi[axis] - lo[axis]) axis = 1;
+    if (hi[2] - lo[2] > hi[axis] - lo[axis]) axis = 2;
+    const double* key = axis == 0 ? sc->cx : (axis == 1 ? sc->cy : sc->cz);
+    const int parts = (n + leaf - 1) / leaf, left = (parts / 2) * leaf;  // the left part is a whole number of leaves
+    std::nth_element(ids.begin() + first, ids.begin() + first + left, ids.begin() + first + n,
+                     [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
+    cluster_split(sc, ids, first, left, leaf, out);
+    cluster_split(sc, ids, first + left, n - left, leaf, out);
+}
+
+float f32_up(double x) {  // smallest float >= x
+    float f = (float)x;
+    return (double)f < x ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f;
+}
+
+ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
+    ClusterHost H;
+    const int n = sc->n;
+    const float finf = std::numeric_limits<float>::infinity(), qnan = std::numeric_limits<float>::quiet_NaN();
+    std::vector<int> pool, always;
+    std::vector<double> rs;
+    auto filterable = [&](int i) {
+        const double cm = std::max(std::fabs(sc->cx[i]), std::max(std::fabs(sc->cy[i]), std::fabs(sc->cz[i])));
+        const double r2 = sc->radius[i] * sc->radius[i];
+        return cm <= 256.0 && r2 <= 256.0;  // false for NaN
+    };
+    for (int i = 0; i < n; i++) {
+        if (filterable(i)) { pool.push_back(i); rs.push_back(std::fabs(sc->radius[i])); } else always.push_back(i);
+    }
+    H.unfilterable = (int)always.size();
+    if (!pool.empty()) {  // a handful of spheres much larger than the typical one: keep their boxes out of the tree
+        std::vector<double> sorted = rs;
+        std::nth_element(sorted.begin(), sorted.begin() + sorted.size() / 2, sorted.end());
+        const double med = sorted[sorted.size() / 2];
+        std::vector<int> big, rest;
+        for (int i : pool) (std::fabs(sc->radius[i]) > 3.0 * med ? big : rest).push_back(i);
+        if (!big.empty() && always.size() + big.size() <= 16) { always.insert(always.end(), big.begin(), big.end()); pool = rest; }
+    }
+    std::sort(always.begin(), always.end());
+    // slot order: real groups (chunks of the pool, group by group), then the always-groups
+    std::vector<std::pair<int, int>> groups, chunks;
+    cluster_split(sc, pool, 0, (int)pool.size(), 64, groups);
+    std::vector<std::vector<int>> chunk_ids;   // [chunk] -> sphere ids (ascending); 8 chunk slots per group
+    std::vector<int> group_first_chunk;
+    for (auto& g : groups) {
+        chunks.clear();
+        cluster_split(sc, pool, g.first, g.second, 8, chunks);
+        group_first_chunk.push_back((int)chunk_ids.size());
+        for (auto& c : chunks) {
+            std::vector<int> v(pool.begin() + c.first, pool.begin() + c.first + c.second);
+            std::sort(v.begin(), v.end());
+            chunk_ids.push_back(v);
+        }
+        while (chunk_ids.size() % 8) chunk_ids.push_back({});
+    }
+    const int used_real_groups = (int)groups.size();
+    H.real_groups = (used_real_groups + 7) / 8 * 8;
+    while ((int)chunk_ids.size() < H.real_groups * 8) chunk_ids.push_back({});
+    H.always_groups = ((int)always.size() + 63) / 64;
+    for (size_t k = 0; k < always.size(); k += 8)
+        chunk_ids.push_back(std::vector<int>(always.begin() + k, always.begin() + std::min(always.size(), k + 8)));
+    {
+        const int last_chunks = ((int)always.size() - (H.always_groups - 1) * 64 + 7) / 8;  // chunks in the last always-group
+        H.always_last = H.always_groups ? (0xffu << (8 - last_chunks)) & 0xffu : 0u;
+    }
+    while (chunk_ids.size() % 8) chunk_ids.push_back({});
+    const int n_chunks = (int)chunk_ids.size(), n_groups_all = n_chunks / 8;
+    // boxes in fp64: exact bounds of the member spheres, padded outwards by 2^-20 relative + a tiny absolute
+    struct Box { double lo[3], hi[3]; bool empty = true, infinite = false; };
+    auto grow_box = [&](Box& b, int i) {
+        if (!filterable(i)) { b.infinite = true; b.empty = false; return; }
+        const double c[3] = {sc->cx[i], sc->cy[i], sc->cz[i]}, r = std::fabs(sc->radius[i]);
+        for (int k = 0; k < 3; k++) {
+            const double pad = (std::fabs(c[k]) + r + 1.0) * 9.6e-7;
+            const double l = c[k] - r - pad, h = c[k] + r + pad;
+            b.lo[k] = b.empty ? l : std::min(b.lo[k], l);
+            b.hi[k] = b.empty ? h : std::max(b.hi[k], h);
+        }
+        b.empty = false;
+    };
+    std::vector<Box> box2(n_chunks), box1(n_groups_all);
+    for (int c = 0; c < n_chunks; c++)
+        for (int i : chunk_ids[c]) { grow_box(box2[c], i); grow_box(box1[c / 8], i); }
+    float rmax = 0.f;
+    auto emit = [&](const Box* b0, const Box* b1, float4* out) {  // one pair of boxes -> three float4 (centre, half extent)
+        float c[2][3], e[2][3];
+        const Box* bs[2] = {b0, b1};
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 3; k++) {
+                const Box* b = bs[j];
+                if (!b || b->empty) { c[j][k] = 0.f; e[j][k] = -finf; continue; }   // never hit
+                if (b->infinite) { c[j][k] = 0.f; e[j][k] = finf; continue; }       // always hit
+                c[j][k] = (float)(0.5 * (b->lo[k] + b->hi[k]));
+                e[j][k] = f32_up(std::max(b->hi[k] - (double)c[j][k], (double)c[j][k] - b->lo[k]));
+                rmax = std::max(rmax, f32_up((double)std::fabs(c[j][k]) + (double)e[j][k]));
+            }
+        out[0] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
+        out[1] = make_float4(c[0][2], c[1][2], e[0][0], e[1][0]);
+        out[2] = make_float4(e[0][1], e[1][1], e[0][2], e[1][2]);
+    };
+    const int f4_pairs = n_chunks * 8, f4_box2 = n_chunks / 2 * 3, f4_box1 = H.real_groups / 2 * 3, f4_ids = (n_chunks * 8 * 2 + 15) / 16;
+    H.off_box2 = f4_pairs; H.off_box1 = H.off_box2 + f4_box2; H.off_ids = H.off_box1 + f4_box1;
+    H.blob.assign((size_t)H.off_ids + f4_ids + 8, make_float4(0, 0, 0, 0));  // + slack: nothing reads past it, kept for safety
+    uint16_t* ids16 = reinterpret_cast<uint16_t*>(H.blob.data() + H.off_ids);
+    float mc = 0.f;
+    for (int c = 0; c < n_chunks; c++) {
+        float cc[8][3], nk[8];
+        for (int u = 0; u < 8; u++) {
+            const bool have = u < (int)chunk_ids[c].size();
+            const int i = have ? chunk_ids[c][u] : -1;
+            ids16[c * 8 + u] = (uint16_t)(have ? i : pad_id);
+            if (!have) { cc[u][0] = cc[u][1] = cc[u][2] = 0.f; nk[u] = -finf; continue; }
+            if (!filterable(i)) { cc[u][0] = cc[u][1] = cc[u][2] = qnan; nk[u] = qnan; continue; }
+            const double r2 = sc->radius[i] * sc->radius[i];
+            cc[u][0] = (float)sc->cx[i]; cc[u][1] = (float)sc->cy[i]; cc[u][2] = (float)sc->cz[i];
+            nk[u] = -(float)((sc->cx[i] * sc->cx[i] + sc->cy[i] * sc->cy[i] + sc->cz[i] * sc->cz[i]) - r2);
+            mc = std::max(mc, (float)std::max(std::fabs(sc->cx[i]), std::max(std::fabs(sc->cy[i]), std::fabs(sc->cz[i]))) * 1.0000002f);
+        }
+        for (int p = 0; p < 4; p++) {  // same pair layout as the linear table: (Cx0,Cx1,Cy0,Cy1), (Cz0,Cz1,-K0,-K1)
+            H.blob[(size_t)c * 8 + 2 * p] = make_float4(cc[2 * p][0], cc[2 * p + 1][0], cc[2 * p][1], cc[2 * p + 1][1]);
+            H.blob[(size_t)c * 8 + 2 * p + 1] = make_float4(cc[2 * p][2], cc[2 * p + 1][2], nk[2 * p], nk[2 * p + 1]);
+        }
+    }
+    for (int c = 0; c < n_chunks; c += 2) emit(&box2[c], &box2[c + 1], H.blob.data() + H.off_box2 + c / 2 * 3);
+    for (int g = 0; g < H.real_groups; g += 2)
+        emit(g < used_real_groups ? &box1[g] : nullptr, g + 1 < used_real_groups ? &box1[g + 1] : nullptr, H.blob.data() + H.off_box1 + g / 2 * 3);
+    H.r = std::max(rmax, mc) * 1.0000002f;
+    return H;
+}
+
+constexpr int kClusterMaxSpheres = 4096;  // 64 groups x 8 chunks x 8 spheres: 8 words of group boxes per segment at most
 constexpr int kBandRows = 8;
 // Scratch budget per pass, in samples (x24 bytes). Whole pixels per pass.
 constexpr unsigned long long kPassSamples = 144ull << 20;  // 88 B per sample (camera ray + colour): <= 13.3 GB of the 180 GB
@@ -619,10 +812,11 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
         const int ch = TRAY_CH > 8 ? TRAY_CH : 8;
         int n = sc->n, n_pad = std::max(ch, (n + ch - 1) / ch * ch);  // the hot loop consumes chunks of TRAY_CH spheres
         const double ninf = -std::numeric_limits<double>::infinity();
-        std::vector<double4> gd(n_pad); std::vector<float4> gf(n_pad);
-        std::vector<double> rd(n_pad, 1.0); std::vector<float> rf(n_pad, 1.0f);
-        std::vector<uint8_t> kd(n_pad, 0); std::vector<double4> pr(n_pad);
-        for (int i = 0; i < n_pad; i++) {
+        const int n_alloc = n_pad + 8;  // entry n is always a never-hit padding entry (the cluster tables point their empty slots at it)
+        std::vector<double4> gd(n_alloc); std::vector<float4> gf(n_alloc);
+        std::vector<double> rd(n_alloc, 1.0); std::vector<float> rf(n_alloc, 1.0f);
+        std::vector<uint8_t> kd(n_alloc, 0); std::vector<double4> pr(n_alloc);
+        for (int i = 0; i < n_alloc; i++) {
             if (i < n) {
                 double r = sc->radius[i];
                 gd[i] = make_double4(sc->cx[i], sc->cy[i], sc->cz[i], r * r);  // Radius*Radius, objects.go:85
@@ -659,6 +853,11 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
             fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nk[0], nk[1]);
         }
+        // two-level cluster tables (the default closest-hit structure up to kClusterMaxSpheres spheres)
+        ClusterHost clh;
+        const bool use_clusters = n <= kClusterMaxSpheres;
+        if (use_clusters) clh = build_clusters(sc, n);
+        ctx->cluster_unfilterable = use_clusters ? clh.unfilterable : n;
         std::vector<int> tree_ids;
         HostBvh hb = bvh_classify(sc, tree_ids);
         // LBVH on the device for large scenes (or when asked for); the host's median-split build otherwise / as fallback
@@ -679,15 +878,23 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             }
             grow(d.fpair, d.cap_fpair, (size_t)n_pad);
             CK(cudaMemcpy(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
-            grow(d.geo_d, d.cap_geo_d, (size_t)n_pad); grow(d.geo_f, d.cap_geo_f, (size_t)n_pad);
-            grow(d.radius_d, d.cap_radius_d, (size_t)n_pad); grow(d.radius_f, d.cap_radius_f, (size_t)n_pad);
-            grow(d.kind, d.cap_kind, (size_t)n_pad); grow(d.params, d.cap_params, (size_t)n_pad);
-            CK(cudaMemcpy(d.geo_d, gd.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.geo_f, gf.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.radius_d, rd.data(), sizeof(double) * n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.radius_f, rf.data(), sizeof(float) * n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.kind, kd.data(), n_pad, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_pad, cudaMemcpyHostToDevice));
+            grow(d.geo_d, d.cap_geo_d, (size_t)n_alloc); grow(d.geo_f, d.cap_geo_f, (size_t)n_alloc);
+            grow(d.radius_d, d.cap_radius_d, (size_t)n_alloc); grow(d.radius_f, d.cap_radius_f, (size_t)n_alloc);
+            grow(d.kind, d.cap_kind, (size_t)n_alloc); grow(d.params, d.cap_params, (size_t)n_alloc);
+            CK(cudaMemcpy(d.geo_d, gd.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.geo_f, gf.data(), sizeof(float4) * n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.radius_d, rd.data(), sizeof(double) * n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.radius_f, rf.data(), sizeof(float) * n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.kind, kd.data(), n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice));
+            d.cl_present = false;
+            if (use_clusters) {
+                grow(d.cl_blob, d.cap_cl_blob, clh.blob.size());
+                CK(cudaMemcpy(d.cl_blob, clh.blob.data(), sizeof(float4) * clh.blob.size(), cudaMemcpyHostToDevice));
+                d.cl_blob_f4 = (int)clh.blob.size(); d.cl_off_box2 = clh.off_box2; d.cl_off_box1 = clh.off_box1; d.cl_off_ids = clh.off_ids;
+                d.cl_real_groups = clh.real_groups; d.cl_always_groups = clh.always_groups; d.cl_always_last = clh.always_last; d.cl_r = clh.r;
+                d.cl_present = true;
+            }
             bool on_device = false;
             if (want_device && !tree_ids.empty()) on_device = bvh_build_device(d, sc, tree_ids);
             if (on_device) ctx->bvh_built_on_device = 1;
@@ -754,7 +961,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     if (p->y0 < 0 || p->y1 > p->height || p->y0 > p->y1) return fail(ctx, TRAY_E_INVALID, "tray_render: bad row range");
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
     if (p->precision < TRAY_FP64_FMA || p->precision > TRAY_FP64_STRICT_BRUTE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad precision");
-    if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_BVH) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
+    if (p->accel < TRAY_ACCEL_AUTO || p->accel > TRAY_ACCEL_CLUSTER) return fail(ctx, TRAY_E_INVALID, "tray_render: bad accel");
     if (p->layout < TRAY_LAYOUT_AUTO || p->layout > TRAY_LAYOUT_WAVEFRONT) return fail(ctx, TRAY_E_INVALID, "tray_render: bad layout");
     if (p->seed == 0) return fail(ctx, TRAY_E_INVALID, "tray_render: seed 0 (the host shim must draw a random seed, ray/tracer.go:32)");
     auto t_start = std::chrono::steady_clock::now();
@@ -882,7 +1089,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     A.spp_local = spp_local; A.sample_stride = stride_s; A.sample_offset = offset_s;
                     A.counter = d.counters + ps; A.scratch = d.scratch; A.stats = d.stats; A.progress = d.stats + 2;
                     A.stk_g = nullptr; A.n_slots = 0; A.gen = nullptr;
-                    const bool wavefront = wavefront_runs(d, p->precision, p->accel, p->layout);  // generates its rays in wf_regen
+                    const bool wavefront = wavefront_runs(ctx, d, p->precision, p->accel, p->layout);  // generates its rays in wf_regen
                     if (!wavefront && !TRAY_GEN_INKERNEL) {
                         grow(d.gen, d.gen_cap, (size_t)A.n_samples);
                         camera_ray_kernel<<<(unsigned)((A.n_samples + 255) / 256), 256, 0, d.stream>>>(A, d.gen);
@@ -931,7 +1138,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->split_mode = p->split_mode;
         if (rgba_out && !subset) copy_out(ctx, rgba_out, stride);
         double kernel_ms = 0, trace_ms = 0;
-        unsigned long long seg = 0, exh = 0, bvh_tests = 0;
+        unsigned long long seg = 0, exh = 0, bvh_tests = 0, box_tests = 0;
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
@@ -944,9 +1151,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             }
             kernel_ms = std::max(kernel_ms, (double)ms);
             trace_ms = std::max(trace_ms, (double)ms2);
-            unsigned long long st[4];
+            unsigned long long st[5];
             CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
-            seg += st[0]; exh += st[1]; bvh_tests += st[3];
+            seg += st[0]; exh += st[1]; bvh_tests += st[3]; box_tests += st[4];
         }
         ctx->have_image = !subset; ctx->have_hdr = true;
         ctx->hdr_is_sums = subset;
@@ -964,8 +1171,10 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             memset(stats, 0, sizeof *stats);
             stats->paths = my_rows * (unsigned long long)p->width * (unsigned long long)(subset ? p->sample_count : p->spp);
             stats->segments = seg;
-            // brute force: every Scene.Hit tests every sphere; BVH: exact tests counted by the kernel
+            // linear scan: every Scene.Hit tests every sphere; BVH: exact tests counted by the kernel; clusters: spheres whose
+            // chunk was scanned (pair pre-filter evaluations), box tests counted separately
             stats->sphere_tests = bvh_tests ? bvh_tests : seg * (unsigned long long)ctx->devs[0].n;
+            stats->box_tests = (double)box_tests;
             stats->depth_exhausted = exh;
             stats->kernel_ms = kernel_ms;
             stats->trace_kernel_ms = trace_ms;

@@ -110,7 +110,10 @@ template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_fl
 //                instructions take them as operands: no LDS, no vector registers for sphere data.
 //   kGeoShared : SoA table staged in shared memory, broadcast LDS.128.
 //   kGeoGlobal : read-only global loads (scenes too large for shared memory).
-enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3, kGeoBVH = 4 };
+//   kGeoFilter : linear scan behind the exact fp32 pair pre-filter (filter_scan).
+//   kGeoBVH    : per-lane BVH traversal (large scenes).
+//   kGeoCluster: two-level boxes over chunks of 8 spheres, warp-uniform, then the pair pre-filter on the marked chunks (cluster_scan).
+enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3, kGeoBVH = 4, kGeoCluster = 5 };
 #ifndef TRAY_PARAM_GEO
 #define TRAY_PARAM_GEO 0
 #endif
@@ -343,6 +346,197 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
     }
 }
 
+// Deferred candidates in ANY order (cluster scan): Sphere.Hit's own root selection (objects.go:90-97) per sphere, the
+// winner by (t, id) lexicographic order -- what the reference's index-order scan with "strictly closer wins" yields
+// (tests/test_unordered_rule_model.py). Divisions whose quotient certainly loses are skipped as in resolve_candidates;
+// the upper bound is strict (fl(x/a) > best_t whenever x >= best_t*a*(1+2^-49)), so a tie with a lower id is never skipped.
+template <typename T, bool FMA, int TPB>
+__device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
+                                                       T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
+    const T tmin = front_epsilon<T>();
+    for (int k = 0; k < ncand; k++) {
+        const int id = cand[k * TPB];
+        typename Vec4T<T>::type g = ggeo[id];
+        T h, c, disc, root;
+        sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+        if (certainly_missed(h, c, disc)) continue;
+        T sq = tsqrt(disc);
+        const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
+        const T hi = best_t * a * up, lo = tmin * a * dn;
+        T x = h - sq;
+        bool ok = false;
+        if (x < hi && x > lo) { root = x / a; ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+        if (!ok) {
+            x = h + sq;
+            if (x < hi && x > lo) { root = x / a; ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+        }
+        if (ok) { best_t = root; best = id; }
+    }
+}
+
+// Two-level closest hit (kGeoCluster, the default for scenes that fit): the spheres are grouped at upload into spatially
+// compact chunks of 8 (recursive median split), 8 chunks form a group. Per ray segment:
+//   1. the boxes of the groups are tested, 8 at a time, with a conservative fp32 slab test (packed FFMA2/FADD2 + FMNMX3);
+//   2. the warp takes the UNION of its lanes' "may hit" bits (REDUX.OR), so everything below stays warp-uniform: table
+//      loads are broadcast LDS.128, no lane waits for another;
+//   3. per marked group the boxes of its 8 chunks are tested the same way, union again;
+//   4. only the marked chunks run the exact fp32 pair pre-filter of filter_scan; survivors are queued and resolved in
+//      fp64 by (t, id) lexicographic order (= the reference's scan order result).
+// Spheres the filter cannot bound (|C| or r^2 > 256, non-finite) and very large ones sit in "always" groups that every
+// ray scans. On the benchmark scene a warp scans about 5 of 62 chunks per segment (tools/cluster_sim.py).
+//
+// The slab test of a box (centre c, half extent e, fp32) for the ray O + d t, d = D/|D|, per axis k:
+//   inv = fl32(1/d_k) (|d_k| clamped to >= 2^-60), nq = -fl32(O_k*inv), ai = |inv|, sl = 12 u R ai   (per ray; u = 2^-24,
+//                                                                     R = max|box coordinate| + |O|inf)
+//   A = fma(c, inv, nq)   B = fma(e, ai, sl)   near = A - B   far = A + B
+//   miss  <=>  min_k far < max_k near  or  min_k far < 0          (sign bits of two words, one LOP3)
+// If the exact ray meets the box at some t* >= 0 then for every axis |(c-O)inv - t*| <= e ai + 1.01 u R ai (inv is the
+// exact reciprocal of a direction within 2u of d_k), A is off by <= 2.01 u R ai (rounding of O*inv and of the fma), B may
+// fall short by u R ai, near/far round by <= 2 u R ai: 6.1 u R ai in all. A hit the strict fp64 Sphere.Hit reports lies
+// within sqrt(160 eps) R = 1.33e-7 R = 2.2 u R of the sphere along the true ray (its discriminant is exact to 20 eps a
+// (|C-O|^2 + r^2)), and the boxes are padded on top of that: 8.3 < 12, so near_k <= t* <= far_k for every k and the test
+// cannot report a miss. tests/test_cluster_box_model.py replays the test in exact single-rounded arithmetic.
+template <typename T, bool FMA, int TPB>
+__device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4* sblob, const typename Vec4T<T>::type* __restrict__ ggeo,
+                                             uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a,
+                                             T& best_t, int& best, int& ncand, unsigned& nchunks, unsigned& nboxes,
+                                             const volatile double* parked = nullptr) {
+    // ---- per-ray constants of the pair pre-filter (same derivation as filter_scan) ----
+    const float u32 = 5.9604645e-8f;
+    const double inv_n = 1.0 / sqrt((double)a);
+    const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
+    const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+    float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+    const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+    const float R = S.cl_r + mo;
+    float eh = 17.5f * u32 * R;
+    float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+                         ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));
+    // origin too far out, or a direction without a finite positive length: no culling at all for this ray
+    const bool off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
+    if (off) { noot = __int_as_float(0x7f800000); eh = 0.0f; }
+    ndo += eh;
+    const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
+    const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
+    const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
+    const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
+    // ---- per-ray constants of the box test ----
+    auto rcp = [](float d) {
+        const float lim = 8.6736174e-19f;  // 2^-60
+        return 1.0f / (fabsf(d) < lim ? copysignf(lim, d) : d);
+    };
+    const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
+    const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
+    const float ks = 12.0f * u32 * R;
+    const float2 IX = make_float2(ix, ix), IY = make_float2(iy, iy), IZ = make_float2(iz, iz);
+    const float2 NQX = make_float2(nqx, nqx), NQY = make_float2(nqy, nqy), NQZ = make_float2(nqz, nqz);
+    const float2 AX = make_float2(fabsf(ix), fabsf(ix)), AY = make_float2(fabsf(iy), fabsf(iy)), AZ = make_float2(fabsf(iz), fabsf(iz));
+    const float2 SX = make_float2(ks * fabsf(ix), ks * fabsf(ix)), SY = make_float2(ks * fabsf(iy), ks * fabsf(iy)),
+                 SZ = make_float2(ks * fabsf(iz), ks * fabsf(iz));
+
+    auto lds4 = [](float4& v, unsigned addr) {
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    };
+    unsigned mask = 0;
+    auto pair = [&](const float4& g0, const float4& g1) {  // two spheres: 8 packed instructions (see filter_scan)
+        const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
+        float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
+        float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);
+        float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
+        float2 v1 = __ffma2_rn(h, h, nc);
+        int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
+        int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
+        mask = __funnelshift_l((unsigned)mx, mask, 1);
+        mask = __funnelshift_l((unsigned)my, mask, 1);
+    };
+    auto boxes = [&](unsigned addr) {  // two boxes: 12 packed instructions + 2 x (2 FMNMX3 + FADD + LOP3 + SHF)
+        float4 b0, b1, b2;
+        lds4(b0, addr); lds4(b1, addr + 16); lds4(b2, addr + 32);
+        const float2 ax = __ffma2_rn(make_float2(b0.x, b0.y), IX, NQX), ay = __ffma2_rn(make_float2(b0.z, b0.w), IY, NQY),
+                     az = __ffma2_rn(make_float2(b1.x, b1.y), IZ, NQZ);
+        const float2 bx = __ffma2_rn(make_float2(b1.z, b1.w), AX, SX), by = __ffma2_rn(make_float2(b2.x, b2.y), AY, SY),
+                     bz = __ffma2_rn(make_float2(b2.z, b2.w), AZ, SZ);
+        const float2 nx = __fadd2_rn(ax, make_float2(-bx.x, -bx.y)), ny = __fadd2_rn(ay, make_float2(-by.x, -by.y)),
+                     nz = __fadd2_rn(az, make_float2(-bz.x, -bz.y));
+        const float2 fx = __fadd2_rn(ax, bx), fy = __fadd2_rn(ay, by), fz = __fadd2_rn(az, bz);
+        const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tf0 = fminf(fminf(fx.x, fy.x), fz.x);
+        const float tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y), tf1 = fminf(fminf(fx.y, fy.y), fz.y);
+        mask = __funnelshift_l((unsigned)(__float_as_int(tf0 - tn0) | __float_as_int(tf0)), mask, 1);
+        mask = __funnelshift_l((unsigned)(__float_as_int(tf1 - tn1) | __float_as_int(tf1)), mask, 1);
+    };
+    auto may_hit8 = [&]() -> unsigned {  // the 8 bits just shifted in -> this lane's "may hit" byte, then the warp's union
+        unsigned hit = off ? 0xffu : (~mask & 0xffu);
+        if (!has) hit = 0u;
+        return __reduce_or_sync(kFull, hit);
+    };
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sblob);
+    const unsigned a_box2 = sbase + (unsigned)S.cl_off_box2 * 16u, a_box1 = sbase + (unsigned)S.cl_off_box1 * 16u;
+    const uint16_t* sids = reinterpret_cast<const uint16_t*>(sblob + S.cl_off_ids);
+    const int n_always = S.cl_always_groups, n_words = S.cl_real_groups >> 3;
+    // words -n_always..-1: one always-group each (no box tests); words 0..: 8 real groups behind their boxes
+#pragma unroll 1
+    for (int w = -n_always; w < n_words; w++) {
+        unsigned ug;
+        int gb;
+        if (w < 0) { ug = 0x80u; gb = S.cl_real_groups + (w + n_always); }
+        else {
+            const unsigned ad = a_box1 + (unsigned)w * (4u * 48u);
+            mask = 0;
+            boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
+            ug = may_hit8();
+            gb = w * 8;
+            nboxes += 8;
+        }
+#pragma unroll 1
+        while (ug) {
+            const int gbit = 31 - __clz(ug);
+            ug &= ~(1u << gbit);
+            const int g = gb + 7 - gbit;
+            unsigned uc;
+            if (w < 0) uc = w == -1 ? S.cl_always_last : 0xffu;
+            else {
+                const unsigned ad = a_box2 + (unsigned)g * (4u * 48u);
+                mask = 0;
+                boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
+                uc = may_hit8();
+                nboxes += 8;
+            }
+#pragma unroll 1
+            while (uc) {
+                const int cbit = 31 - __clz(uc);
+                uc &= ~(1u << cbit);
+                const int chunk = g * 8 + 7 - cbit;
+                const unsigned ad = sbase + (unsigned)chunk * 128u;
+                float4 a0, a1, a2, a3, b0, b1, b2, b3;
+                lds4(a0, ad); lds4(a1, ad + 16); lds4(a2, ad + 32); lds4(a3, ad + 48);
+                lds4(b0, ad + 64); lds4(b1, ad + 80); lds4(b2, ad + 96); lds4(b3, ad + 112);
+                mask = 0;
+                pair(a0, a1); pair(a2, a3); pair(b0, b1); pair(b2, b3);
+                nchunks++;
+                unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
+                if (m) {
+                    if (ncand > kCand - 8) {  // list about to overflow (rare): run the exact test on what is queued
+                        if (parked) {
+                            const T px_ = T(parked[0]), py_ = T(parked[TPB]), pz_ = T(parked[2 * TPB]);
+                            const T qx_ = T(parked[3 * TPB]), qy_ = T(parked[4 * TPB]), qz_ = T(parked[5 * TPB]);
+                            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, px_, py_, pz_, qx_, qy_, qz_, (qx_ * qx_ + qy_ * qy_) + qz_ * qz_, best_t, best);
+                        } else {
+                            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+                        }
+                        ncand = 0;
+                    }
+                    do {  // bit 7-u <-> slot chunk*8+u
+                        const int bit = 31 - __clz(m);
+                        cand[ncand * TPB] = sids[chunk * 8 + 7 - bit];
+                        ncand++;
+                        m &= ~(1u << bit);
+                    } while (m);
+                }
+            }
+        }
+    }
+}
+
 // Exchange area of the regroup layout (one per CTA, shared memory): the path state of every lane, SoA.
 template <int TPB>
 struct RegroupBuf {
@@ -364,8 +558,9 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     constexpr int CH = TRAY_CH;  // spheres per candidate-mask chunk (n_pad is a multiple of 8)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T4* sgeo = reinterpret_cast<T4*>(smem_raw);
-    const size_t geo_bytes = GEO == kGeoShared ? (size_t)S.n_pad * sizeof(T4) : (GEO == kGeoFilter ? (size_t)S.n_pad * 16 : 0);
-    float4* sfp = reinterpret_cast<float4*>(smem_raw);  // kGeoFilter: n_pad/2 pairs x 2 float4
+    const size_t geo_bytes = GEO == kGeoShared ? (size_t)S.n_pad * sizeof(T4)
+                           : (GEO == kGeoFilter ? (size_t)S.n_pad * 16 : (GEO == kGeoCluster ? (size_t)S.cl_blob_f4 * 16 : 0));
+    float4* sfp = reinterpret_cast<float4*>(smem_raw);  // kGeoFilter: n_pad/2 pairs x 2 float4; kGeoCluster: the cluster blob
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
     const size_t pool_off = (geo_bytes + sizeof(ZigTables) + (size_t)kCand * TPB * sizeof(uint16_t) + 15) & ~(size_t)15;
@@ -376,6 +571,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         for (int i = tid; i < S.n_pad; i += TPB) sgeo[i] = S.geo[i];
     if (GEO == kGeoFilter)
         for (int i = tid; i < S.n_pad; i += TPB) sfp[i] = S.fpair[i];
+    if (GEO == kGeoCluster)
+        for (int i = tid; i < S.cl_blob_f4; i += TPB) sfp[i] = S.cl_blob[i];
     zig_load(zig, tid, TPB);
     __syncthreads();
     const T4* __restrict__ ggeo = S.geo;
@@ -395,8 +592,8 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
     int depth_left = 0, sp = 0;
     uint16_t stk[REGROUP ? 1 : kMaxDepth];
     unsigned slot = blockIdx.x * TPB + tid;  // regroup layout: where this path's attenuation stack lives
-    unsigned long long nseg = 0, ntests = 0;
-    unsigned nexh = 0, ndone = 0, ntests_blk = 0;
+    unsigned long long nseg = 0, ntests = 0, nbox = 0;
+    unsigned nexh = 0, ndone = 0, ntests_blk = 0, nbox_blk = 0;
     const int n_pad = S.n_pad;
 
     for (;;) {
@@ -480,7 +677,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         __shared__ int s_parki[3][TPB];
         volatile double* pk = &s_park[0][tid];
         volatile int* pki = &s_parki[0][tid];
-        constexpr bool kPark = GEO == kGeoFilter && !REGROUP;
+        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster) && !REGROUP;
         if constexpr (kPark) {
             pk[0] = (double)O.x; pk[TPB] = (double)O.y; pk[2 * TPB] = (double)O.z;
             pk[3 * TPB] = (double)D.x; pk[4 * TPB] = (double)D.y; pk[5 * TPB] = (double)D.z;
@@ -495,9 +692,13 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         if constexpr (GEO == kGeoBVH) {
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
             if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
-        } else if constexpr (GEO == kGeoFilter) {
+        } else if constexpr (GEO == kGeoFilter || GEO == kGeoCluster) {
+            unsigned nchunks = 0, nboxes = 0;
+            (void)nchunks; (void)nboxes;
 #if TRAY_PARK_STATE
             if constexpr (kPark) {
+                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, nchunks, nboxes, pk);
+                else
                 filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pk);
                 ox = T(pk[0]); oy = T(pk[TPB]); oz = T(pk[2 * TPB]); dx = T(pk[3 * TPB]); dy = T(pk[4 * TPB]); dz = T(pk[5 * TPB]);
                 a = (dx * dx + dy * dy) + dz * dz;
@@ -506,7 +707,15 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                 depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
             } else
 #endif
-            filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
+            {
+                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, nchunks, nboxes);
+                else filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
+            }
+            if constexpr (GEO == kGeoCluster) {
+                if (has) { ntests_blk += 8u * nchunks; nbox_blk += nboxes; }
+                if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
+                if (nbox_blk > 0x40000000u) { nbox += nbox_blk; nbox_blk = 0; }
+            }
         } else {
         // Branch-free body: every test contributes one bit ("may be hit") to the chunk mask through a funnel
         // shift. The mask of chunk k is examined while chunk k+1 is in flight, so no branch waits on FP64 results.
@@ -529,9 +738,13 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             mask_prev = mask;
         }
         }
-        if (mask_prev)
-            push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
-        resolve_candidates<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+        if constexpr (GEO == kGeoCluster) {
+            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+        } else {
+            if (mask_prev)
+                push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
+            resolve_candidates<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+        }
         }
 
         // ---------------- regroup: sort the CTA's paths by what happens next ----------------
@@ -652,8 +865,10 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
 
     // stats: warp-reduce, one atomic per warp
     ntests += ntests_blk;
+    nbox += nbox_blk;
     for (int off = 16; off > 0; off >>= 1) {
         ntests += __shfl_down_sync(kFull, ntests, off);
+        nbox += __shfl_down_sync(kFull, nbox, off);
         nseg += __shfl_down_sync(kFull, nseg, off);
         nexh += __shfl_down_sync(kFull, nexh, off);
         ndone += __shfl_down_sync(kFull, ndone, off);
@@ -662,6 +877,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         atomicAdd(&A.stats[0], nseg);
         atomicAdd(&A.stats[1], (unsigned long long)nexh);
         if (ntests) atomicAdd(&A.stats[3], ntests);
+        if (nbox) atomicAdd(&A.stats[4], nbox);
         if (A.progress) atomicAdd(A.progress, (unsigned long long)ndone);
     }
 }

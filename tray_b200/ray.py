@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from . import rand  # noqa: F401  (fortio.org/rand host side: rand.New / rand.NewIdx)
 from ._lib import LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, LAYOUT_WAVEFRONT, SUMS_ACCUMULATE, SUMS_OFF, SUMS_OVERWRITE  # noqa: F401
-from ._lib import ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, FP32, FP64_FMA, FP64_STRICT, FP64_STRICT_BRUTE, SPLIT_SAMPLES, SPLIT_TILES, STREAM_PER_SAMPLE, STREAM_REFERENCE, TrayError  # noqa: F401
+from ._lib import ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER, FP32, FP64_FMA, FP64_STRICT, FP64_STRICT_BRUTE, SPLIT_SAMPLES, SPLIT_TILES, STREAM_PER_SAMPLE, STREAM_REFERENCE, TrayError  # noqa: F401
 
 # ------------------------------------------------------------------------------------------------
 # Vec3 helpers (ray/vec3.go) on plain 3-tuples; op order as in the reference
