@@ -18,6 +18,7 @@
  *   tray_resolve_sums  <- the tail of RenderLines   ray/tracer.go:145-152 (colorSum * 1/N, ToSRGBA, Pix store)
  *   tray_present       <- draw.BiLinear/NearestNeighbor.Scale + ap.ShowScaledImage   main.go:119-130 (tray's OnResize tail)
  *   tray_configure     <- (no reference counterpart: where the closest-hit BVH of a large scene is built)
+ *   tray_cluster_tables <- Scene.Hit           ray/objects.go:37-46 (the structure that replaces the linear scan; host-only probe)
  *   tray_encode_png    <- SaveImage / png.Encode    main.go:26-36, benchmark/benchmark.go:23-33
  *   tray_upload_frame  <- (no reference counterpart: an image the context did not render, for present / PNG / tests)
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
@@ -175,6 +176,14 @@ TRAY_API int tray_abi_version(void);
 #define TRAY_BVH_BUILD_DEVICE 2
 TRAY_API int tray_configure(tray_ctx *ctx, int32_t key, int64_t value);
 TRAY_API int64_t tray_query(tray_ctx *ctx, int32_t key);
+
+/* Device-free (host code only, no CUDA call): the two-level cluster tables tray_scene_upload stages for TRAY_ACCEL_CLUSTER,
+ * for tests and inspection. Layout of the blob (float4 units): pair pre-filter table in slot order (8 float4 per chunk of 8
+ * slots) | chunk boxes from meta[1] (three float4 per pair of chunks: centre, half extent) | group boxes from meta[2] | uint16
+ * sphere id per slot from meta[3]. meta = {blob float4s, off_box2, off_box1, off_ids, real groups (multiple of 8), always-groups,
+ * chunk mask of the last always-group, spheres the filter cannot bound}; r_out = max |coordinate| the error bounds assume.
+ * Copies at most cap_floats floats; blob_out may be NULL (size query). Scene.Hit reference: ray/objects.go:37-46. */
+TRAY_API int tray_cluster_tables(const tray_scene_desc *scene, float *blob_out, size_t cap_floats, int32_t *meta, float *r_out);
 
 /* Copies the scene to every device of the context. May be called again to replace the scene. */
 TRAY_API int tray_scene_upload(tray_ctx *ctx, const tray_scene_desc *scene);

@@ -135,7 +135,11 @@ def test_config1_image_and_hdr_bit_exact(ctx, O, precision, fma):
     assert np.array_equal(img, ref)
     assert np.array_equal(ctx.read_hdr(w, h), hdr)
     assert t.Stats["segments"] == st["segments"] and t.Stats["paths"] == st["paths"] == w * h * spp
-    assert t.Stats["depth_exhausted"] == st["max_depth_hits"] and t.Stats["sphere_tests"] == st["sphere_tests"]
+    assert t.Stats["depth_exhausted"] == st["max_depth_hits"]
+    if precision == ray.FP64_STRICT:  # default closest-hit structure: two-level clusters, a fraction of the spheres is looked at
+        assert 0 < t.Stats["sphere_tests"] < st["sphere_tests"] / 4 and t.Stats["box_tests"] > 0
+    else:                             # all-fp64 kernels scan linearly: Scene.Hit's N tests per segment
+        assert t.Stats["sphere_tests"] == st["sphere_tests"]
 
 
 def test_golden_fixture_without_oracle(ctx):
@@ -273,15 +277,17 @@ def test_bvh_and_brute_force_agree_bit_for_bit(ctx, O):
     ref, hdr, st = O.render(O.rich_scene(2), O.camera_init(w, h, **O.RICH_CAMERA),
                             O.make_params(w, h, spp=spp, max_depth=depth, seed=2, num_workers=8, stream_mode=1), want_hdr=True)
     tests = {}
-    for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH):
+    for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH, ray.ACCEL_CLUSTER):
         for precision in (ray.FP64_STRICT, ray.FP64_STRICT_BRUTE):
             t = tracer(w, h, spp, depth, precision=precision)
             t.Accel = accel
             img = t.Render(scene)
             assert np.array_equal(img, ref) and np.array_equal(ctx.read_hdr(w, h), hdr), (accel, precision)
             assert t.Stats["segments"] == st["segments"]
-            tests[accel] = t.Stats["sphere_tests"]
-    assert tests[ray.ACCEL_BRUTE] == st["sphere_tests"] and tests[ray.ACCEL_BVH] < tests[ray.ACCEL_BRUTE] / 10
+            tests[accel, precision] = t.Stats["sphere_tests"]
+    S, B = ray.FP64_STRICT, ray.FP64_STRICT_BRUTE
+    assert tests[ray.ACCEL_BRUTE, S] == tests[ray.ACCEL_BRUTE, B] == tests[ray.ACCEL_CLUSTER, B] == st["sphere_tests"]  # (the all-fp64 kernel has no cluster form)
+    assert tests[ray.ACCEL_BVH, S] < st["sphere_tests"] / 10 and tests[ray.ACCEL_CLUSTER, S] < st["sphere_tests"] / 4
 
 
 def test_bvh_ties_nested_and_degenerate_scenes(ctx, O):
@@ -295,7 +301,7 @@ def test_bvh_ties_nested_and_degenerate_scenes(ctx, O):
     }
     for name, objs in scenes.items():
         scene = ray.Scene(list(objs), ray.DefaultBackground())
-        for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH):
+        for accel in (ray.ACCEL_BRUTE, ray.ACCEL_BVH, ray.ACCEL_CLUSTER):
             t = tracer(61, 33, 3, 30, seed=5, cam=ray.Camera(VerticalFoV=40.0))
             t.Accel = accel
             img = t.Render(scene).copy()
@@ -422,7 +428,7 @@ def test_layouts_are_bit_identical(ctx, w, h, spp, depth):
         ib = b.Render(scene).copy()
         hb = ctx.read_hdr(w, h)
         assert np.array_equal(ia, ib) and np.array_equal(ha, hb), layout
-        for k in ("paths", "segments", "sphere_tests", "depth_exhausted"):
+        for k in ("paths", "segments", "depth_exhausted"):  # (sphere_tests counts the chunks a WARP scans: it depends on who shares a warp)
             assert a.Stats[k] == b.Stats[k], (layout, k)
 
 
@@ -468,8 +474,8 @@ def _random_scene(rs, n, scale, shift):
 @pytest.mark.parametrize("seed,n,scale,shift", [(1, 40, 1.0, 0.0), (2, 150, 5.0, 3.0), (3, 500, 30.0, -100.0), (4, 60, 200.0, 0.0),
                                                  (5, 30, 1e-3, 0.0), (6, 90, 3.0, 250.0), (7, 700, 12.0, 0.0), (8, 25, 1e4, 0.0)])
 def test_prefilter_never_changes_a_result_on_random_scenes(ctx, seed, n, scale, shift):
-    """Images, linear-HDR means and segment counts of the default kernel (pre-filter, regroup layout), of the plain and
-    wavefront layouts and of the BVH must equal the all-fp64 linear scan bit for bit, whatever the scene looks like --
+    """Images, linear-HDR means and segment counts of the default kernel (two-level clusters + pre-filter), of the linear
+    pre-filter scan in the plain, regroup and wavefront layouts and of the BVH must equal the all-fp64 linear scan bit for bit, whatever the scene looks like --
     including cameras inside spheres, spheres beyond the filter's table range and origins far from the scene."""
     rs = np.random.RandomState(seed)
     scene = _random_scene(rs, n, scale, shift)
@@ -482,7 +488,10 @@ def test_prefilter_never_changes_a_result_on_random_scenes(ctx, seed, n, scale, 
                                            ("filter+regroup", ray.FP64_STRICT, ray.LAYOUT_REGROUP, ray.ACCEL_BRUTE),
                                            ("filter+plain", ray.FP64_STRICT, ray.LAYOUT_PLAIN, ray.ACCEL_BRUTE),
                                            ("wavefront", ray.FP64_STRICT, ray.LAYOUT_WAVEFRONT, ray.ACCEL_BRUTE),
-                                           ("bvh", ray.FP64_STRICT, ray.LAYOUT_AUTO, ray.ACCEL_BVH)):
+                                           ("bvh", ray.FP64_STRICT, ray.LAYOUT_AUTO, ray.ACCEL_BVH),
+                                           ("default", ray.FP64_STRICT, ray.LAYOUT_AUTO, ray.ACCEL_AUTO),
+                                           ("cluster+plain", ray.FP64_STRICT, ray.LAYOUT_PLAIN, ray.ACCEL_CLUSTER),
+                                           ("cluster+regroup", ray.FP64_STRICT, ray.LAYOUT_REGROUP, ray.ACCEL_CLUSTER)):
         t = tracer(w, h, spp, depth, seed=seed, precision=precision, cam=cam)
         t.RayRadius = 0.5
         t.Layout, t.Accel = layout, accel

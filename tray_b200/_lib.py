@@ -19,7 +19,8 @@ CFG_BVH_BUILD, BVH_BUILD_AUTO, BVH_BUILD_HOST, BVH_BUILD_DEVICE = 1, 0, 1, 2
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
-           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png", "tray_configure", "tray_query", "tray_upload_frame")
+           "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png", "tray_configure", "tray_query", "tray_upload_frame",
+           "tray_cluster_tables")
 
 
 class TrayError(RuntimeError):
@@ -116,6 +117,7 @@ def lib():
         L.tray_query.argtypes = [C.c_void_p, C.c_int32]
         L.tray_query.restype = C.c_int64
         L.tray_upload_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
+        L.tray_cluster_tables.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.tray_progress.argtypes = [C.c_void_p]
         L.tray_progress.restype = C.c_uint64
         L.tray_measure_peak.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -1237,6 +1237,18 @@ int tray_read_hdr(tray_ctx* ctx, double* hdr_out) {
     return TRAY_OK;
 }
 
+int tray_cluster_tables(const tray_scene_desc* sc, float* blob_out, size_t cap_floats, int32_t* meta, float* r_out) {
+    if (!sc || !meta || sc->n < 0 || sc->n > 65535 || (sc->n > 0 && (!sc->cx || !sc->cy || !sc->cz || !sc->radius))) return TRAY_E_INVALID;
+    try {
+        ClusterHost H = build_clusters(sc, sc->n);
+        meta[0] = (int32_t)H.blob.size(); meta[1] = H.off_box2; meta[2] = H.off_box1; meta[3] = H.off_ids;
+        meta[4] = H.real_groups; meta[5] = H.always_groups; meta[6] = (int32_t)H.always_last; meta[7] = H.unfilterable;
+        if (r_out) *r_out = H.r;
+        if (blob_out) memcpy(blob_out, H.blob.data(), std::min(cap_floats, H.blob.size() * 4) * sizeof(float));
+    } catch (const std::exception&) { return TRAY_E_INVALID; }
+    return TRAY_OK;
+}
+
 int tray_configure(tray_ctx* ctx, int32_t key, int64_t value) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);

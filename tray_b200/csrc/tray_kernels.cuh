@@ -143,10 +143,10 @@ __device__ __forceinline__ void resolve_candidates(const typename Vec4T<T>::type
         const T hi = best_t * a * up, lo = tmin * a * dn;
         T x = h - sq;
         bool ok = false;
-        if (x < hi && x > lo) { root = x / a; ok = root > tmin && root < best_t; }
+        if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && root < best_t; }
         if (!ok) {
             x = h + sq;
-            if (x < hi && x > lo) { root = x / a; ok = root > tmin && root < best_t; }
+            if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && root < best_t; }
         }
         if (ok) { best_t = root; best = id; }
     }
@@ -187,9 +187,9 @@ __device__ __forceinline__ void exact_test_unordered(const typename Vec4T<T>::ty
     if (disc < T(0)) return;
     const T tmin = front_epsilon<T>();
     T sq = tsqrt(disc);
-    T root = (h - sq) / a;
+    T root = tdiv(h - sq, a);
     if (!(root > tmin)) {
-        root = (h + sq) / a;
+        root = tdiv(h + sq, a);
         if (!(root > tmin)) return;
     }
     if (root < best_t || (root == best_t && id < best)) { best_t = root; best = id; }
@@ -365,13 +365,25 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
         const T hi = best_t * a * up, lo = tmin * a * dn;
         T x = h - sq;
         bool ok = false;
-        if (x < hi && x > lo) { root = x / a; ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+        if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
         if (!ok) {
             x = h + sq;
-            if (x < hi && x > lo) { root = x / a; ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+            if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
         }
         if (ok) { best_t = root; best = id; }
     }
+}
+
+// The rare in-scan flush of a full candidate list: one out-of-line copy (results in registers), so that the scan's hot
+// code stays small.
+template <typename T> struct BestHit { T t; int id; };
+template <typename T, bool FMA, int TPB>
+__device__ __noinline__ BestHit<T> flush_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
+                                                        T ox, T oy, T oz, T dx, T dy, T dz, T best_t, int best) {
+    resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, (dx * dx + dy * dy) + dz * dz, best_t, best);
+    BestHit<T> r;
+    r.t = best_t; r.id = best;
+    return r;
 }
 
 // Two-level closest hit (kGeoCluster, the default for scenes that fit): the spheres are grouped at upload into spatially
@@ -403,7 +415,7 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                                              const volatile double* parked = nullptr) {
     // ---- per-ray constants of the pair pre-filter (same derivation as filter_scan) ----
     const float u32 = 5.9604645e-8f;
-    const double inv_n = 1.0 / sqrt((double)a);
+    const double inv_n = div_f64(1.0, sqrt_f64((double)a));
     const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
     const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
     float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
@@ -473,36 +485,18 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     const unsigned a_box2 = sbase + (unsigned)S.cl_off_box2 * 16u, a_box1 = sbase + (unsigned)S.cl_off_box1 * 16u;
     const uint16_t* sids = reinterpret_cast<const uint16_t*>(sblob + S.cl_off_ids);
     const int n_always = S.cl_always_groups, n_words = S.cl_real_groups >> 3;
-    // words -n_always..-1: one always-group each (no box tests); words 0..: 8 real groups behind their boxes
+    // words -n_always..-1: one always-group each (no box tests); words 0..: 8 real groups behind their boxes.
+    // One code site tests 8 boxes (a word of groups or the chunks of a group), one site scans a chunk: the walk is written
+    // as a loop that decides what comes next, so that the hot code is 104 + 70 instructions instead of two copies of each.
 #pragma unroll 1
     for (int w = -n_always; w < n_words; w++) {
-        unsigned ug;
-        int gb;
-        if (w < 0) { ug = 0x80u; gb = S.cl_real_groups + (w + n_always); }
-        else {
-            const unsigned ad = a_box1 + (unsigned)w * (4u * 48u);
-            mask = 0;
-            boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
-            ug = may_hit8();
-            gb = w * 8;
-            nboxes += 8;
-        }
+        unsigned ug = 0, uc = 0;   // warp-uniform: groups of this word / chunks of group g still to visit
+        int g = 0;
+        bool word_done = false;    // the word's own boxes have been tested
+        if (w < 0) { g = S.cl_real_groups + (w + n_always); uc = w == -1 ? S.cl_always_last : 0xffu; word_done = true; }
 #pragma unroll 1
-        while (ug) {
-            const int gbit = 31 - __clz(ug);
-            ug &= ~(1u << gbit);
-            const int g = gb + 7 - gbit;
-            unsigned uc;
-            if (w < 0) uc = w == -1 ? S.cl_always_last : 0xffu;
-            else {
-                const unsigned ad = a_box2 + (unsigned)g * (4u * 48u);
-                mask = 0;
-                boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
-                uc = may_hit8();
-                nboxes += 8;
-            }
-#pragma unroll 1
-            while (uc) {
+        for (;;) {
+            if (uc) {
                 const int cbit = 31 - __clz(uc);
                 uc &= ~(1u << cbit);
                 const int chunk = g * 8 + 7 - cbit;
@@ -516,13 +510,13 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                 unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
                 if (m) {
                     if (ncand > kCand - 8) {  // list about to overflow (rare): run the exact test on what is queued
-                        if (parked) {
-                            const T px_ = T(parked[0]), py_ = T(parked[TPB]), pz_ = T(parked[2 * TPB]);
-                            const T qx_ = T(parked[3 * TPB]), qy_ = T(parked[4 * TPB]), qz_ = T(parked[5 * TPB]);
-                            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, px_, py_, pz_, qx_, qy_, qz_, (qx_ * qx_ + qy_ * qy_) + qz_ * qz_, best_t, best);
-                        } else {
-                            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+                        T fx_ = ox, fy_ = oy, fz_ = oz, gx_ = dx, gy_ = dy, gz_ = dz;
+                        if (parked) {  // TRAY_PARK_STATE: the fp64 ray waits in shared memory during the scan
+                            fx_ = T(parked[0]); fy_ = T(parked[TPB]); fz_ = T(parked[2 * TPB]);
+                            gx_ = T(parked[3 * TPB]); gy_ = T(parked[4 * TPB]); gz_ = T(parked[5 * TPB]);
                         }
+                        const BestHit<T> bh = flush_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, fx_, fy_, fz_, gx_, gy_, gz_, best_t, best);
+                        best_t = bh.t; best = bh.id;
                         ncand = 0;
                     }
                     do {  // bit 7-u <-> slot chunk*8+u
@@ -532,7 +526,22 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                         m &= ~(1u << bit);
                     } while (m);
                 }
+                continue;
             }
+            unsigned ad;
+            if (!word_done) ad = a_box1 + (unsigned)w * (4u * 48u);
+            else {
+                if (!ug) break;
+                const int gbit = 31 - __clz(ug);
+                ug &= ~(1u << gbit);
+                g = w * 8 + 7 - gbit;
+                ad = a_box2 + (unsigned)g * (4u * 48u);
+            }
+            mask = 0;
+            boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
+            const unsigned u8 = may_hit8();
+            nboxes += 8;
+            if (!word_done) { ug = u8; word_done = true; } else uc = u8;
         }
     }
 }
@@ -824,7 +833,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                     scattered = dot(D2, N) > T(0);
                 } else {  // Dielectric.Scatter, materials.go:44-64
                     T ri = T(prm.x);
-                    T ratio = front ? T(1) / ri : ri;
+                    T ratio = front ? tdiv(T(1), ri) : ri;
                     T cosTheta = tmin2(dot(vneg(ud), N), T(1));
                     T sinTheta = tsqrt(T(1) - cosTheta * cosTheta);
                     bool refl = ratio * sinTheta > T(1);
