@@ -144,10 +144,22 @@ func (t *Tracer) renderCUDA(scene *Scene, y0, y1, idx int) error {
 	if err := f.walk(scene.Objects); err != nil {
 		return err
 	}
+	// tray_scene_desc holds POINTERS to the SoA arrays. cgo only lets C see a Go pointer to memory that itself contains Go
+	// pointers when those inner pointers are pinned (cgocheck: "Go pointer to unpinned Go pointer" panics otherwise), so the
+	// backing arrays are pinned for the duration of the upload (runtime.Pinner, Go >= 1.21; the module requires go 1.24).
+	// The library copies everything before tray_scene_upload returns and keeps no caller pointer.
+	var pin runtime.Pinner
+	defer pin.Unpin()
 	var sd C.tray_scene_desc
 	sd.n = C.int32_t(len(f.cx))
-	sd.cx, sd.cy, sd.cz, sd.radius, sd.mat_params = ptrF(f.cx), ptrF(f.cy), ptrF(f.cz), ptrF(f.r), ptrF(f.params)
-	if len(f.kind) > 0 {
+	if len(f.cx) > 0 {
+		pin.Pin(&f.cx[0])
+		pin.Pin(&f.cy[0])
+		pin.Pin(&f.cz[0])
+		pin.Pin(&f.r[0])
+		pin.Pin(&f.params[0])
+		pin.Pin(&f.kind[0])
+		sd.cx, sd.cy, sd.cz, sd.radius, sd.mat_params = ptrF(f.cx), ptrF(f.cy), ptrF(f.cz), ptrF(f.r), ptrF(f.params)
 		sd.mat_kind = (*C.uint8_t)(unsafe.Pointer(&f.kind[0]))
 	}
 	v3(&sd.bg_a, scene.Background.ColorA)

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -145,9 +146,27 @@ struct Device {
     unsigned long long* stats = nullptr;     // [0] segments [1] depth exhausted [2] progress samples
     double* srgb_thr = nullptr;
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;
+    // tray_progress: a side stream and a pinned word per device (another thread peeks at the counters of a render in flight)
+    cudaStream_t peek_stream = nullptr;
+    unsigned long long* peek_host = nullptr;
+    // in-context sample split: can device 0 read this device's memory (peer access over NVLink)? If not, its partial sums
+    // are staged into a buffer on device 0 with cudaMemcpyPeerAsync before the combine kernel.
+    bool peer_of_root = true;
+    double* stage = nullptr; size_t stage_cap = 0;   // lives on device 0, one per non-peer device
     // last render bookkeeping
     std::vector<int> local_rows;  // global row of each local row
     int passes = 0;
+    bool timed = false;           // ev_begin / ev_end were recorded by the last render
+};
+
+// Frees a temporary device allocation on every exit path (the parity probes allocate per call).
+struct DevTmp {
+    void* p = nullptr;
+    explicit DevTmp(size_t bytes) { CK(cudaMalloc(&p, bytes ? bytes : 1)); }
+    ~DevTmp() { cudaFree(p); }
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    template <typename P> P* as() const { return static_cast<P*>(p); }
 };
 
 cudaEvent_t next_event(Device& d) {
@@ -191,8 +210,7 @@ struct tray_ctx {
     std::atomic<uint64_t> progress_base{0};
     std::atomic<int> progress_spp{1};
     std::atomic<bool> rendering{false};
-    cudaStream_t peek_stream = nullptr;
-    unsigned long long* peek_host = nullptr;
+    std::mutex peek_mu;                // tray_progress callers take turns on the per-device pinned words
 };
 
 namespace {
@@ -754,20 +772,24 @@ int tray_init(const int* devices, int n_devices, tray_ctx** out) {
             CK(cudaMemcpyToSymbol(g_zig_fn, ZIG_FN_INIT, sizeof(float) * 128));
             ctx->devs.push_back(d);
         }
-        // peer access for the sample-split combine (root reads peers' partial sums over NVLink)
+        // peer access for the sample-split combine (root reads peers' partial sums over NVLink); without it the sums are staged
         for (size_t i = 1; i < ctx->devs.size(); i++) {
             int can = 0;
             CK(cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[i].dev));
+            ctx->devs[i].peer_of_root = false;
             if (can) {
                 CK(cudaSetDevice(ctx->devs[0].dev));
                 cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->devs[i].dev, 0);
-                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) ctx->devs[i].peer_of_root = true;
                 cudaGetLastError();
             }
         }
+        for (Device& d : ctx->devs) {
+            CK(cudaSetDevice(d.dev));
+            CK(cudaStreamCreateWithFlags(&d.peek_stream, cudaStreamNonBlocking));
+            CK(cudaHostAlloc(&d.peek_host, sizeof(unsigned long long), cudaHostAllocDefault));
+        }
         CK(cudaSetDevice(ctx->devs[0].dev));
-        CK(cudaStreamCreateWithFlags(&ctx->peek_stream, cudaStreamNonBlocking));
-        CK(cudaHostAlloc(&ctx->peek_host, sizeof(unsigned long long), cudaHostAllocDefault));
     } catch (const std::exception& ex) {
         g_init_error = ex.what();
         tray_destroy(ctx);
@@ -794,9 +816,11 @@ void tray_destroy(tray_ctx* ctx) {
         for (cudaEvent_t e : d.ev_pool) cudaEventDestroy(e);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.peek_stream) cudaStreamDestroy(d.peek_stream);
+        if (d.peek_host) cudaFreeHost(d.peek_host);
     }
-    if (ctx->peek_stream) cudaStreamDestroy(ctx->peek_stream);
-    if (ctx->peek_host) cudaFreeHost(ctx->peek_host);
+    for (Device& d : ctx->devs)
+        if (d.stage) { cudaSetDevice(ctx->devs[0].dev); cudaFree(d.stage); }
     delete ctx;
 }
 
@@ -955,8 +979,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!cam || !p) return fail(ctx, TRAY_E_INVALID, "tray_render: null camera/params");
     if (!ctx->have_scene) return fail(ctx, TRAY_E_NO_SCENE, "tray_render: no scene uploaded");
-    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth <= 0)
-        return fail(ctx, TRAY_E_INVALID, "tray_render: width/height/spp/max_depth must be > 0 (apply Tracer defaults on the host)");
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth < 0)
+        return fail(ctx, TRAY_E_INVALID, "tray_render: width/height/spp must be > 0 and max_depth >= 0 (apply Tracer defaults on the host)");
+    if (p->stream_mode != TRAY_STREAM_REFERENCE && p->stream_mode != TRAY_STREAM_PER_SAMPLE) return fail(ctx, TRAY_E_INVALID, "tray_render: bad stream_mode");
     if (p->max_depth > kMaxDepth) return fail(ctx, TRAY_E_UNSUPPORTED, "tray_render: max_depth > 256");
     if (p->y0 < 0 || p->y1 > p->height || p->y0 > p->y1) return fail(ctx, TRAY_E_INVALID, "tray_render: bad row range");
     if (rgba_out && stride < (size_t)p->width * 4) return fail(ctx, TRAY_E_INVALID, "tray_render: stride < 4*width");
@@ -976,7 +1001,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->width = p->width; ctx->height = p->height; ctx->y0 = p->y0; ctx->y1 = p->y1;
         ctx->have_image = false; ctx->have_hdr = false;
         ctx->progress_base = 0; ctx->progress_spp = p->spp; ctx->rendering = true;
-        for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; d.ev_used = 0; }
+        for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; d.ev_used = 0; d.timed = false; }
         DevCamera dcam = dev_camera(cam);
         const int ext_count = p->shard_count > 1 ? p->shard_count : 1;
         const int ext_index = p->shard_count > 1 ? p->shard_index : 0;
@@ -1005,7 +1030,12 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             A.rgba = d.rgba; A.hdr = d.hdr; A.srgb_thr = d.srgb_thr; A.stats = d.stats;
             CK(cudaMemsetAsync(d.stats, 0, 8 * sizeof(unsigned long long), d.stream));
             CK(cudaEventRecord(d.ev_begin, d.stream));
-            if (rows > 0) {
+            d.timed = true;
+            if (rows > 0 && p->max_depth == 0) {
+                black_kernel<<<(unsigned)((px + 255) / 256), 256, 0, d.stream>>>(d.rgba, d.hdr, px);
+                CK(cudaGetLastError());
+                launches++;
+            } else if (rows > 0) {
                 CK(cudaEventRecord(next_event(d), d.stream));
                 size_t smem = (size_t)d.n_pad * sizeof(double4) + sizeof(ZigTables);
                 DevScene<double> S = dev_scene<double>(ctx, d);
@@ -1028,6 +1058,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             const bool split_samples = (p->split_mode == TRAY_SPLIT_SAMPLES) && G > 1;
             if (split_samples && ext_count > 1) throw std::runtime_error("tray_render: sample split cannot be combined with external shards");
             if (subset) {
+                if (p->max_depth == 0) throw std::runtime_error("tray_render: sums_mode needs max_depth > 0");
                 if (split_samples) throw std::runtime_error("tray_render: sums_mode cannot be combined with the in-context sample split");
                 if (p->sample_stride < 1 || p->sample_count < 1 || p->sample_offset < 0 ||
                     (long long)p->sample_offset + (long long)(p->sample_count - 1) * p->sample_stride >= (long long)p->spp)
@@ -1061,8 +1092,16 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                 grow(d.rgba, d.rgba_cap, std::max<size_t>(n_pixels * 4, 4));
                 grow(d.hdr, d.hdr_cap, std::max<size_t>(n_pixels * 3, 3));
                 CK(cudaEventRecord(d.ev_begin, d.stream));
+                d.timed = true;
                 if (n_pixels == 0 || spp_local == 0) {
                     if (split_samples && n_pixels) CK(cudaMemsetAsync(d.hdr, 0, n_pixels * 3 * sizeof(double), d.stream));
+                    CK(cudaEventRecord(d.ev_end, d.stream));
+                    continue;
+                }
+                if (p->max_depth == 0) {  // every sample is black; in the sample split the combine kernel turns the zero sums into pixels
+                    black_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, d.stream>>>(d.rgba, d.hdr, n_pixels);
+                    CK(cudaGetLastError());
+                    launches++;
                     CK(cudaEventRecord(d.ev_end, d.stream));
                     continue;
                 }
@@ -1119,7 +1158,15 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                 CK(cudaSetDevice(d0.dev));
                 const unsigned long long n_pixels = (unsigned long long)d0.local_rows.size() * p->width;
                 CombineArgs C;
-                for (int g = 0; g < G; g++) C.partial[g] = ctx->devs[g].hdr;
+                for (int g = 0; g < G; g++) {
+                    Device& dg = ctx->devs[g];
+                    C.partial[g] = dg.hdr;
+                    if (g > 0 && !dg.peer_of_root && n_pixels) {  // no peer mapping: bring the partial sums over with a peer copy
+                        grow(dg.stage, dg.stage_cap, (size_t)n_pixels * 3);
+                        CK(cudaMemcpyPeerAsync(dg.stage, d0.dev, dg.hdr, dg.dev, n_pixels * 3 * sizeof(double), d0.stream));
+                        C.partial[g] = dg.stage;
+                    }
+                }
                 C.n_parts = G; C.n_pixels = n_pixels; C.inv_spp = 1.0 / (double)p->spp;
                 C.rgba = d0.rgba; C.srgb_thr = d0.srgb_thr;
                 // combine in place is not possible (hdr is an input): reuse scratch for the mean
@@ -1142,6 +1189,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
+            if (!d.timed) continue;  // (reference streams run on device 0 only: the other devices of the context did nothing)
             float ms = 0, ms2 = 0;
             CK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
             for (int e = 0; e + 1 < d.ev_used; e += 2) {
@@ -1310,8 +1358,8 @@ int tray_first_hit(tray_ctx* ctx, const tray_camera* cam, int32_t width, int32_t
         Device& d = ctx->devs[0];
         CK(cudaSetDevice(d.dev));
         size_t n = (size_t)width * height;
-        int* d_id; double *d_t, *d_n; unsigned char* d_f;
-        CK(cudaMalloc(&d_id, n * 4)); CK(cudaMalloc(&d_t, n * 8)); CK(cudaMalloc(&d_n, n * 24)); CK(cudaMalloc(&d_f, n));
+        DevTmp t_id(n * 4), t_t(n * 8), t_n(n * 24), t_f(n);  // freed on every exit path
+        int* d_id = t_id.as<int>(); double* d_t = t_t.as<double>(); double* d_n = t_n.as<double>(); unsigned char* d_f = t_f.as<unsigned char>();
         DevCamera dc = dev_camera(cam);
         unsigned blocks = (unsigned)((n + 127) / 128);
         if (precision == TRAY_FP64_FMA) first_hit_kernel<double, true><<<blocks, 128, 0, d.stream>>>(dc, dev_scene<double>(ctx, d), width, height, d_id, d_t, d_n, d_f);
@@ -1321,7 +1369,6 @@ int tray_first_hit(tray_ctx* ctx, const tray_camera* cam, int32_t width, int32_t
         CK(cudaStreamSynchronize(d.stream));
         CK(cudaMemcpy(id, d_id, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(t, d_t, n * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(normal, d_n, n * 24, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(front, d_f, n, cudaMemcpyDeviceToHost));
-        cudaFree(d_id); cudaFree(d_t); cudaFree(d_n); cudaFree(d_f);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
 }
@@ -1334,13 +1381,12 @@ int tray_rng_dump(tray_ctx* ctx, int32_t kind, uint64_t idx, uint64_t seed, doub
         Device& d = ctx->devs[0];
         CK(cudaSetDevice(d.dev));
         int per = kind == 3 ? 3 : (kind == 4 ? 2 : 1);
-        double* dout;
-        CK(cudaMalloc(&dout, sizeof(double) * n * per));
+        DevTmp tmp(sizeof(double) * n * per);
+        double* dout = tmp.as<double>();
         rng_dump_kernel<<<1, 128, 0, d.stream>>>(kind, idx, seed, radius, n, dout);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d.stream));
         CK(cudaMemcpy(out, dout, sizeof(double) * n * per, cudaMemcpyDeviceToHost));
-        cudaFree(dout);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
 }
@@ -1352,14 +1398,13 @@ int tray_linear_to_srgb(tray_ctx* ctx, const double* x, int32_t n, uint8_t* out)
     try {
         Device& d = ctx->devs[0];
         CK(cudaSetDevice(d.dev));
-        double* dx; unsigned char* dout;
-        CK(cudaMalloc(&dx, sizeof(double) * n)); CK(cudaMalloc(&dout, n));
+        DevTmp t_x(sizeof(double) * n), t_o(n);
+        double* dx = t_x.as<double>(); unsigned char* dout = t_o.as<unsigned char>();
         CK(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
         srgb_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(dx, n, d.srgb_thr, dout);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d.stream));
         CK(cudaMemcpy(out, dout, n, cudaMemcpyDeviceToHost));
-        cudaFree(dx); cudaFree(dout);
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
     return TRAY_OK;
 }
@@ -1434,9 +1479,11 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
         // tile mode on several devices: gather the row bands onto device 0 (peer copies over NVLink), still no host pixels
         const uchar4* frame = reinterpret_cast<const uchar4*>(d.rgba);
         unsigned char* gathered = nullptr;
+        std::unique_ptr<DevTmp> gathered_mem;  // freed on every exit path
         if ((int)d.local_rows.size() != ctx->height) {
             const size_t row_bytes = (size_t)ctx->width * 4;
-            CK(cudaMalloc(&gathered, row_bytes * ctx->height));
+            gathered_mem.reset(new DevTmp(row_bytes * ctx->height));
+            gathered = gathered_mem->as<unsigned char>();
             for (Device& dv : ctx->devs) {
                 size_t r = 0, nrows = dv.local_rows.size();
                 while (r < nrows) {
@@ -1502,7 +1549,6 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
             if (cap < ht.file_bytes) rc = fail(ctx, TRAY_E_INVALID, "tray_encode_png: png_out too small (png_len holds the size needed)");
             else CK(cudaMemcpy(png_out, out, (size_t)ht.file_bytes, cudaMemcpyDeviceToHost));
         }
-        cudaFree(gathered);
         return rc;
     } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
 }
@@ -1510,13 +1556,14 @@ int tray_encode_png(tray_ctx* ctx, uint8_t* png_out, size_t cap, size_t* png_len
 uint64_t tray_progress(tray_ctx* ctx) {
     if (!ctx) return 0;
     if (!ctx->rendering.load()) return ctx->progress_base.load();
-    // render in flight (another thread holds ctx->mu): peek at the device counters on a side stream
+    // render in flight (another thread holds ctx->mu): peek at the device counters on each device's side stream
+    std::lock_guard<std::mutex> lock(ctx->peek_mu);
     uint64_t samples = 0;
     for (Device& d : ctx->devs) {
         if (cudaSetDevice(d.dev) != cudaSuccess) continue;
-        if (cudaMemcpyAsync(ctx->peek_host, d.stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->peek_stream) != cudaSuccess) continue;
-        if (cudaStreamSynchronize(ctx->peek_stream) != cudaSuccess) continue;
-        samples += *ctx->peek_host;
+        if (cudaMemcpyAsync(d.peek_host, d.stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.peek_stream) != cudaSuccess) continue;
+        if (cudaStreamSynchronize(d.peek_stream) != cudaSuccess) continue;
+        samples += *d.peek_host;
     }
     int spp = ctx->progress_spp.load();
     return samples / (uint64_t)(spp > 0 ? spp : 1);

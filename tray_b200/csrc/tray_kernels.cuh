@@ -210,6 +210,7 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
     const bool cull = fmax(fabs(o[0]), fmax(fabs(o[1]), fabs(o[2]))) < 1048576.0 * (S.bvh_extent + 1.0);
     int stack[48];
     int sp = 0;
+    bool overflow = false;
     stack[sp++] = 0;
     while (sp > 0) {
         const BvhNode nd = S.bvh[stack[--sp]];
@@ -234,8 +235,14 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
             if (sp <= 46) {
                 stack[sp++] = neg ? nd.left : nd.right;
                 stack[sp++] = neg ? nd.right : nd.left;
-            }
+            } else overflow = true;
         }
+    }
+    // A tree deeper than the stack (the builders reject those today): never drop a subtree silently -- test every sphere
+    // instead (the (t, id) rule makes repeated tests harmless). Slow, correct.
+    if (overflow) {
+        ntests += S.n;
+        for (int i = 0; i < S.n; i++) exact_test_unordered<T, FMA>(ggeo, i, ox, oy, oz, dx, dy, dz, a, best_t, best);
     }
 }
 
@@ -354,7 +361,8 @@ template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                        T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
     const T tmin = front_epsilon<T>();
-    for (int k = 0; k < ncand; k++) {
+#pragma unroll 1
+    for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
         const int id = cand[k * TPB];
         typename Vec4T<T>::type g = ggeo[id];
         T h, c, disc, root;
@@ -435,7 +443,7 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     // ---- per-ray constants of the box test ----
     auto rcp = [](float d) {
         const float lim = 8.6736174e-19f;  // 2^-60
-        return 1.0f / (fabsf(d) < lim ? copysignf(lim, d) : d);
+        return rcp_f32(fabsf(d) < lim ? copysignf(lim, d) : d);
     };
     const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
     const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
@@ -928,6 +936,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs R) {
     px.z = linear_to_srgb(R.srgb_thr, cz);
     px.w = 255;
     reinterpret_cast<uchar4*>(R.rgba)[lp] = px;
+}
+
+// MaxDepth == 0: RayColor returns black for every sample (ray/objects.go:50-52), the pixel is (0,0,0,255).
+__global__ void __launch_bounds__(256) black_kernel(unsigned char* rgba, double* hdr, unsigned long long n_pixels) {
+    unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    reinterpret_cast<uchar4*>(rgba)[p] = make_uchar4(0, 0, 0, 255);
+    hdr[3 * p] = 0.0; hdr[3 * p + 1] = 0.0; hdr[3 * p + 2] = 0.0;
 }
 
 // Sample-split epilogue: sum the per-device partial sums (peer pointers over NVLink, device order),
