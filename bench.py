@@ -150,6 +150,46 @@ def cpu_port_step(cp):
     return img, st, dt
 
 
+def oracle_rows_check(workload, host_img, target_seconds, threads, rate_hint=None):
+    """Parity spot check: a bounded set of rows y == off (mod step) of `workload` rendered by the CPU oracle (strict fp64,
+    per-sample streams) and compared with the same rows of the GPU image. Returns (parity dict, cpu stats)."""
+    from oracle import oracle as O
+    w, h, spp, depth, half, _ = WORKLOADS[workload]
+    scene = O.rich_scene(SEED, half)
+    cam = O.camera_init(w, h, **O.RICH_CAMERA)
+    p = O.make_params(w, h, spp=spp, max_depth=depth, seed=SEED, num_workers=threads, stream_mode=1, fma_mode=0)
+    if rate_hint is None:  # calibrate on one row in the middle of the image
+        t0 = time.perf_counter()
+        _, st = O.render_sampled_rows(scene, cam, p, h, h // 2, threads)
+        rate_hint = st["paths"] / max(time.perf_counter() - t0, 1e-6)
+    rows = int(max(1, min(h, target_seconds * rate_hint / (w * spp))))
+    step = max(1, h // rows)
+    off = step // 2
+    t0 = time.perf_counter()
+    img, st = O.render_sampled_rows(scene, cam, p, step, off, threads)
+    dt = time.perf_counter() - t0
+    ys = list(range(off, h, step))
+    d = np.abs(img[ys, :, :3].astype(np.int16) - host_img[ys, :, :3].astype(np.int16)).max(axis=2)
+    parity = {"rows_checked": len(ys), "pixels_identical_frac": float((d == 0).mean()), "pixels_within_1lsb_frac": float((d <= 1).mean()),
+              "mode": "GPU fp64 vs strict CPU port (oracle), rows y%%%d==%d" % (step, off)}
+    return parity, {"paths": st["paths"], "seconds": dt, "threads": threads}
+
+
+def ncu_summary():
+    """Pipe utilisation and where the time goes, from the committed `ncu --set full` capture of the default kernel
+    (profiles/r*_trace_kernel_summary.json, written by tools/summarize_profiles.py); None when there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(_ROOT, "profiles", "r*_trace_kernel_summary.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+        d["source"] = os.path.basename(files[-1])
+        return d
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU algorithm (oracle port; Go cannot be built here) on all host
     threads, same metric/config, each step a bounded sample of the workload."""
@@ -198,32 +238,48 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; tray_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers: ranks that wait must not keep a kernel spinning on their GPU
 
     workload = args.workload or ("config2" if args.gpus == 1 else "config3")
     w, h, spp, depth, half, desc = WORKLOADS[workload]
     PREC = {"fp64": ray.FP64_STRICT, "fp64-brute": ray.FP64_STRICT_BRUTE, "fp64-fma": ray.FP64_FMA, "fp32": ray.FP32}
     precision = PREC[args.precision]
+    LAYOUTS = {"auto": ray.LAYOUT_AUTO, "plain": ray.LAYOUT_PLAIN, "regroup": ray.LAYOUT_REGROUP, "wavefront": ray.LAYOUT_WAVEFRONT}
 
     ctx = ray.Context([local_rank])
-    scene = ray.RichScene(rand.New(SEED), half)
-    tr = ray.New(w, h)
-    tr.Camera = ray.RichSceneCamera()
-    tr.MaxDepth, tr.NumRaysPerPixel, tr.Seed, tr.Precision = depth, spp, SEED, precision
-    tr.Layout = {"auto": ray.LAYOUT_AUTO, "plain": ray.LAYOUT_PLAIN, "regroup": ray.LAYOUT_REGROUP, "wavefront": ray.LAYOUT_WAVEFRONT}[args.layout]
+
+    def job(name, shard=(0, 0)):
+        """Scene, camera and params of a workload on this rank's context (Tracer.Render's defaulting: ray/tracer.go:49-83)."""
+        jw, jh, jspp, jdepth, jhalf, _ = WORKLOADS[name]
+        sc = ray.RichScene(rand.New(SEED), jhalf)
+        t = ray.New(jw, jh)
+        t.Camera = ray.RichSceneCamera()
+        t.MaxDepth, t.NumRaysPerPixel, t.Seed, t.Precision = jdepth, jspp, SEED, precision
+        t.Layout = LAYOUTS[args.layout]
+        t.ShardIndex, t.ShardCount = shard
+        t.Context = ctx
+        t._prepare(sc)
+        return t, sc.flatten()
+
     split_samples = args.split == "samples" and world > 1
-    tr.ShardIndex, tr.ShardCount = (rank, world) if (world > 1 and not split_samples) else (0, 0)
-    tr.Context = ctx
-    tr._prepare(scene)  # Tracer.Render's defaulting: default background, Camera.Initialize (ray/tracer.go:49-83)
-    flat = scene.flatten()
+    tr, flat = job(workload, (rank, world) if (world > 1 and not split_samples) else (0, 0))
     n_spheres = len(flat["cx"])
     ctx.upload(flat)
     cam_c = tr.to_c()
     params = tr._params(0, h)
+
+    def sample_params():
+        q = tr._params(0, h)
+        q.shard_index, q.shard_count = 0, 0
+        q.sample_offset, q.sample_stride, q.sample_count = multi.sample_subset(spp, rank, world)
+        q.sums_mode = ray.SUMS_OVERWRITE
+        return q
+
     if split_samples:  # rank r traces samples s == r (mod world) of every pixel; sums reduced to rank 0 with NCCL
-        params.sample_offset, params.sample_stride, params.sample_count = multi.sample_subset(spp, rank, world)
-        params.sums_mode = ray.SUMS_OVERWRITE
+        params = sample_params()
 
     # shared host image for the e2e leg (each rank writes its own row bands; no collective)
     if world > 1:
@@ -242,6 +298,11 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def host_barrier():
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
 
     def max_over_ranks(x):
         if world == 1:
@@ -263,11 +324,11 @@ def run_ours(args):
     def exchange(out_img=None):
         """Sample split: the one exchange step -- sum-reduce of the fp64 colour sums to rank 0 (NCCL over NVLink), then
         1/N + sRGB on rank 0. Returns the device time of the reduce on torch's stream (CUDA events)."""
-        if sums_t[0] is None:
-            ptr, n = ctx.device_sums()
-            sums_t[0] = torch.as_tensor(multi._DeviceBuffer(ptr, n), device=torch.device("cuda", local_rank))
+        ptr, n = ctx.device_sums()
+        if sums_t[0] is None or sums_t[0][0] != (ptr, n):
+            sums_t[0] = ((ptr, n), torch.as_tensor(multi._DeviceBuffer(ptr, n), device=torch.device("cuda", local_rank)))
         ev[0].record()
-        dist.reduce(sums_t[0], dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(sums_t[0][1], dst=0, op=dist.ReduceOp.SUM)
         ev[1].record()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -279,6 +340,21 @@ def run_ours(args):
     peak_strict_tf, _ = ctx.measure_peak(1)
     peak_f32_tf, _ = ctx.measure_peak(2)
 
+    def timed_steps(cam, prm, steps, with_exchange=False):
+        """`steps` device-resident renders (scene in HBM, image left in HBM), L2 flushed in between; library CUDA events."""
+        acc = dict(ms=0.0, trace_ms=0.0, launches=0, segments=0, paths=0, trace_launches=0, sphere_tests=0, box_tests=0.0, exchange_ms=0.0)
+        for _ in range(steps):
+            flush_buf.zero_()  # L2 flush between timed iterations (outside the event-timed kernels)
+            torch.cuda.synchronize()
+            st = ctx.render(cam, prm, None)
+            acc["ms"] += st["kernel_ms"]; acc["trace_ms"] += st["trace_kernel_ms"]; acc["launches"] += st["launches"]
+            if with_exchange:
+                xms = exchange()
+                acc["ms"] += xms; acc["exchange_ms"] += xms; acc["launches"] += 1
+            acc["segments"] += st["segments"]; acc["paths"] += st["paths"]; acc["trace_launches"] += int(st["trace_launches"])
+            acc["sphere_tests"] += st["sphere_tests"]; acc["box_tests"] += st["box_tests"]
+        return acc
+
     # ---- device-resident leg ----
     for _ in range(max(args.warmup, 3)):  # timing rules: at least 3 warm-up steps
         ctx.render(cam_c, params, None)
@@ -288,27 +364,21 @@ def run_ours(args):
     sync_all()
     sampler.start()
     wall0 = time.perf_counter()
-    dev_ms, trace_ms, launches, segments, paths, trace_launches, sphere_tests = 0.0, 0.0, 0, 0, 0, 0, 0
-    exchange_ms = 0.0
-    for _ in range(args.steps):
-        flush_buf.zero_()  # L2 flush between timed iterations (outside the event-timed kernels)
-        torch.cuda.synchronize()
-        st = ctx.render(cam_c, params, None)
-        dev_ms += st["kernel_ms"]; trace_ms += st["trace_kernel_ms"]; launches += st["launches"]
-        if split_samples:
-            xms = exchange()
-            dev_ms += xms; exchange_ms += xms; launches += 1
-        segments += st["segments"]; paths += st["paths"]; trace_launches += int(st["trace_launches"]); sphere_tests += st["sphere_tests"]
+    m = timed_steps(cam_c, params, args.steps, split_samples)
     sync_all()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop()
+    dev_ms, trace_ms, launches, segments, paths = m["ms"], m["trace_ms"], m["launches"], m["segments"], m["paths"]
+    trace_launches, sphere_tests, box_tests, exchange_ms = m["trace_launches"], m["sphere_tests"], m["box_tests"], m["exchange_ms"]
     dev_ms = max_over_ranks(dev_ms)
     all_paths = sum_over_ranks(paths)
     all_segments = sum_over_ranks(segments)
     value = all_paths / (dev_ms * 1e-3) / 1e6
-    # roofline of the dominant kernel (trace_kernel) on this rank
-    flops = algorithmic_flops(segments, n_spheres, sphere_tests)
-    uses_bvh = sphere_tests < segments * n_spheres
+    # roofline of the dominant kernel (trace_kernel) on this rank. SURVEY 8(d) counts the work of the REFERENCE algorithm:
+    # every Scene.Hit tests every sphere (18 flops each); the default kernel answers the same question looking at a few
+    # per cent of them, so `achieved` is reference-equivalent work per second, not instructions executed on the FP64 pipe.
+    flops = algorithmic_flops(segments, n_spheres)
+    structure = "linear scan" if sphere_tests >= segments * n_spheres else ("two-level clusters" if box_tests > 0 else "bvh")
     achieved_tf = flops / (trace_ms * 1e-3) / 1e12 if trace_ms > 0 else 0.0
     peak_used = {"fp64": peak_tf, "fp64-brute": peak_tf, "fp64-fma": peak_tf, "fp32": peak_f32_tf}[args.precision]
     peak_ffma2_tf = ctx.measure_peak(5)[0]
@@ -319,9 +389,10 @@ def run_ours(args):
 
     # ---- the other fp64 kernels, reported beside the default (same steps, device-resident) ----
     alts = []
+    frac_fp64_brute = None
     if args.precision == "fp64" and not args.no_alt and not split_samples:
-        notes = {"fp64-brute": "same strict arithmetic, every test on the FP64 pipe (no pre-filter): 17 FP64 instructions per 18-flop test, "
-                               "structural ceiling 0.529 of the DFMA peak",
+        notes = {"fp64-brute": "same strict arithmetic, every test on the FP64 pipe (no pre-filter, linear scan): 17 FP64 instructions per 18-flop test, "
+                               "structural ceiling 0.529 of the DFMA peak -- the kernel that actually sits on the FP64 roofline",
                  "fp64-fma": "Sphere.Hit discriminant with fused multiply-add (11 FP64 instructions/test, ceiling 0.818), no pre-filter; image "
                              "identical at 8 bits, first-hit ids exact, t within 3e-12, normals within 4e-11 of the strict result"}
         for name in ("fp64-brute", "fp64-fma"):
@@ -329,13 +400,12 @@ def run_ours(args):
             p2.precision = PREC[name]
             for _ in range(2):
                 ctx.render(cam_c, p2, None)
-            a_ms, a_trace, a_seg, a_paths = 0.0, 0.0, 0, 0
-            for _ in range(args.steps):
-                st2 = ctx.render(cam_c, p2, None)
-                a_ms += st2["kernel_ms"]; a_trace += st2["trace_kernel_ms"]; a_seg += st2["segments"]; a_paths += st2["paths"]
-            a_ms = max_over_ranks(a_ms)
-            a_tf = algorithmic_flops(a_seg, n_spheres) / (a_trace * 1e-3) / 1e12
-            alts.append({"precision": name, "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+            a = timed_steps(cam_c, p2, args.steps)
+            a_ms = max_over_ranks(a["ms"])
+            a_tf = algorithmic_flops(a["segments"], n_spheres) / (a["trace_ms"] * 1e-3) / 1e12
+            if name == "fp64-brute":
+                frac_fp64_brute = a_tf / peak_tf
+            alts.append({"precision": name, "value": sum_over_ranks(a["paths"]) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
                          "roofline": {"bound": "fp64", "achieved": a_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": a_tf / peak_tf},
                          "note": notes[name]})
         # same default arithmetic, other divergence layout / closest-hit structure (results bit-identical)
@@ -343,22 +413,19 @@ def run_ours(args):
                 ("fp64, regroup layout", lambda q: setattr(q, "layout", ray.LAYOUT_REGROUP),
                  "default kernel plus per-material regrouping of the CTA's paths through shared memory after every Scene.Hit (TRAY_LAYOUT_REGROUP)"),
                 ("fp64, wavefront layout", lambda q: setattr(q, "layout", ray.LAYOUT_WAVEFRONT),
-                 "path state in HBM, one bounce = intersect | shade over per-material queues | regenerate kernels (TRAY_LAYOUT_WAVEFRONT)"),
+                 "path state in HBM, one bounce = intersect | shade over per-material queues | regenerate kernels (TRAY_LAYOUT_WAVEFRONT; linear pre-filter scan)"),
                 ("fp64, linear scan", lambda q: setattr(q, "accel", ray.ACCEL_BRUTE),
                  "round-1 default: every sphere of the table through the exact fp32 pair pre-filter, reference order (TRAY_ACCEL_BRUTE)"),
                 ("fp64, bvh", lambda q: setattr(q, "accel", ray.ACCEL_BVH),
-                 "small BVH instead of the linear scan (TRAY_ACCEL_BVH): far fewer sphere tests, so no roofline claim; image bit-identical")):
+                 "per-lane BVH traversal instead of the warp-wide cluster boxes (TRAY_ACCEL_BVH); image bit-identical")):
             p2 = tr._params(0, h)
             setp(p2)
             for _ in range(2):
                 ctx.render(cam_c, p2, None)
-            a_ms, a_paths, a_tests, a_seg = 0.0, 0, 0, 0
-            for _ in range(args.steps):
-                st2 = ctx.render(cam_c, p2, None)
-                a_ms += st2["kernel_ms"]; a_paths += st2["paths"]; a_tests += st2["sphere_tests"]; a_seg += st2["segments"]
-            a_ms = max_over_ranks(a_ms)
-            alts.append({"precision": name, "value": sum_over_ranks(a_paths) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
-                         "sphere_tests_per_segment": a_tests / max(1, a_seg), "note": note})
+            a = timed_steps(cam_c, p2, args.steps)
+            a_ms = max_over_ranks(a["ms"])
+            alts.append({"precision": name, "value": sum_over_ranks(a["paths"]) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+                         "sphere_tests_per_segment": a["sphere_tests"] / max(1, a["segments"]), "note": note})
         # fp32 fast path: throughput + PSNR of its 8-bit image against the fp64 image (same streams)
         if world == 1:
             p3 = tr._params(0, h)
@@ -367,48 +434,54 @@ def run_ours(args):
             img32 = np.zeros((h, w, 4), dtype=np.uint8)
             ctx.render(cam_c, params, img64)
             ctx.render(cam_c, p3, img32)
-            f_ms, f_paths = 0.0, 0
-            for _ in range(args.steps):
-                st3 = ctx.render(cam_c, p3, None)
-                f_ms += st3["kernel_ms"]; f_paths += st3["paths"]
+            f = timed_steps(cam_c, p3, args.steps)
             mse = float(((img64[:, :, :3].astype(np.float64) - img32[:, :, :3].astype(np.float64)) ** 2).mean())
-            alts.append({"precision": "fp32", "value": f_paths / (f_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+            alts.append({"precision": "fp32", "value": f["paths"] / (f["ms"] * 1e-3) / 1e6, "unit": "Mpaths/s",
                          "psnr_db_vs_fp64": (10 * np.log10(255.0 ** 2 / mse)) if mse > 0 else None,
                          "pixels_within_1lsb_frac": float((np.abs(img64.astype(np.int16) - img32.astype(np.int16)).max(axis=2) <= 1).mean()),
                          "note": "float32 arithmetic end to end (same RNG streams, FrontEpsilon 1e-3 instead of 1e-6); no parity claim"})
 
     # ---- end-to-end leg: host buffers, scene H2D + image D2H inside the timed region ----
-    interactive = workload == "config5" and world == 1  # tray's OnResize body: Render + downscale + ANSI frame (main.go:89-137)
     term_cols, term_rows = 160, 45
-    ansi_bytes = 0
 
-    def e2e_step():
-        nonlocal ansi_bytes
-        ctx.upload(flat)
-        if interactive:
-            st_ = ctx.render(cam_c, params, None)                       # frame stays in HBM
-            frame, _, _ = ctx.present(term_cols, term_rows * 2, want_image=False)  # BiLinear s=4 + half-block ANSI on device
-            ansi_bytes = len(frame)
-        elif split_samples:
-            st_ = ctx.render(cam_c, params, None)
-            exchange(host_img)
-        else:
-            st_ = ctx.render(cam_c, params, host_img)
-        return st_
+    def e2e_run(cam, prm, fl, img, steps, warm, interactive=False, with_exchange=False):
+        """The reference-facing call sequence with HOST buffers every step. interactive: tray's OnResize body (main.go:89-137)
+        = Render + downscale + ANSI frame on the device, only the ANSI bytes come back."""
+        ansi = [0]
 
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    e_paths = 0
-    for _ in range(args.steps):
-        st = e2e_step()
-        e_paths += st["paths"]
-    sync_all()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    e2e_value = sum_over_ranks(e_paths) / (e2e_ms * 1e-3) / 1e6
-    h2d = sum(flat[k].nbytes for k in ("cx", "cy", "cz", "r", "kind", "params")) + 48 + \
-        __import__("ctypes").sizeof(_lib.CameraC) + __import__("ctypes").sizeof(_lib.Params)
+        def step():
+            ctx.upload(fl)
+            if interactive:
+                st_ = ctx.render(cam, prm, None)                                         # frame stays in HBM
+                frame, _, _ = ctx.present(term_cols, term_rows * 2, want_image=False)    # BiLinear s=4 + half-block ANSI on device
+                ansi[0] = len(frame)
+            elif with_exchange:
+                st_ = ctx.render(cam, prm, None)
+                exchange(img)
+            else:
+                st_ = ctx.render(cam, prm, img)
+            return st_
+        for _ in range(warm):
+            step()
+        sync_all()
+        t0 = time.perf_counter()
+        n_paths, st_ = 0, None
+        for _ in range(steps):
+            st_ = step()
+            n_paths += st_["paths"]
+        sync_all()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return sum_over_ranks(n_paths) / (ms * 1e-3) / 1e6, ms / steps, st_, ansi[0]
+
+    def h2d_bytes(fl):
+        return int(sum(fl[k].nbytes for k in ("cx", "cy", "cz", "r", "kind", "params")) + 48 +
+                   __import__("ctypes").sizeof(_lib.CameraC) + __import__("ctypes").sizeof(_lib.Params))
+
+    interactive = workload == "config5" and world == 1
+    e2e_value, e2e_ms_step, st, ansi_bytes = e2e_run(cam_c, params, flat, host_img, args.steps, min(args.warmup, 2), interactive, split_samples)
+    if interactive:
+        ctx.read_image(host_img)  # the frame stayed in HBM (only the ANSI bytes crossed PCIe): fetch it for the parity check below
+    h2d = h2d_bytes(flat)
     my_rows = st["paths"] // (w * spp)
     d2h = int(ansi_bytes) if interactive else (int(h * w * 4) if split_samples else int(my_rows * w * 4))
 
@@ -435,10 +508,82 @@ def run_ours(args):
             save_png["cpu_pillow_ms"] = None
             save_png["cpu_note"] = str(e)
 
+    threads = host_threads()
+    # ---- N > 1: the other multi-GPU variants, after the main timed legs ----
+    multi_gpu = {}
+    if world > 1 and not args.no_alt:
+        main_img = np.array(host_img) if rank == 0 else None  # the multi-process tile image (all ranks' rows are in after sync_all)
+        # (c) sample split + NCCL sum-reduce, a short leg on all ranks (skipped when it IS the main mode)
+        if not split_samples and spp >= world:
+            ps = sample_params()
+            ctx.render(cam_c, ps, None); exchange()
+            sync_all()
+            a = timed_steps(cam_c, ps, 2, True)
+            a_ms = max_over_ranks(a["ms"])
+            img_s = np.zeros((h, w, 4), dtype=np.uint8) if rank == 0 else None
+            ctx.render(cam_c, ps, None); exchange(img_s)
+            rec = {"precision": "fp64, samples%d+nccl_reduce" % world, "value": sum_over_ranks(a["paths"]) / (a_ms * 1e-3) / 1e6, "unit": "Mpaths/s",
+                   "exchange": {"collective": "NCCL reduce(sum) to rank 0 + resolve", "bytes": int(w) * h * 24, "ms_per_step": a["exchange_ms"] / 2},
+                   "note": "rank r traces samples s == r (mod N) of every pixel; ONE exchange step: fp64 colour sums (w*h*3 doubles) reduced in place "
+                           "on the library's device buffer, rank 0 applies 1/N + sRGB (bench.py --split samples makes this the main mode)"}
+            if rank == 0:
+                dd = np.abs(img_s[:, :, :3].astype(np.int16) - main_img[:, :, :3].astype(np.int16)).max(axis=2)
+                rec["vs_tiles_image"] = {"pixels_identical_frac": float((dd == 0).mean()), "pixels_within_1lsb_frac": float((dd <= 1).mean())}
+                rec["within_2pct_of_tiles"] = bool(abs(rec["value"] / value - 1) <= 0.02)
+            alts.append(rec)
+        host_barrier()
+        if rank == 0:
+            # (a) config-size parity: strided rows of the multi-process image against the CPU oracle
+            try:
+                multi_gpu["parity"], _ = oracle_rows_check(workload, main_img, 6.0, threads)
+            except Exception as e:
+                multi_gpu["parity_error"] = str(e)
+            # (b) ONE process, ONE context over all N devices: what the cgo shim's TRAY_GPUS uses (Tracer.Render's fan-out,
+            #     ray/tracer.go:85-116): interleaved tiles, and the sample split with combine_kernel over peer memory
+            try:
+                ctx_g = ray.Context(list(range(world)))
+                ctx_g.upload(flat)
+                inctx = {}
+                for name, split in (("tiles", ray.SPLIT_TILES), ("samples", ray.SPLIT_SAMPLES)):
+                    pg = tr._params(0, h)
+                    pg.shard_index, pg.shard_count, pg.split_mode = 0, 0, split
+                    img_g = np.zeros((h, w, 4), dtype=np.uint8)
+                    ctx_g.render(cam_c, pg, None)
+                    g_ms, g_paths, k = 0.0, 0, 2
+                    for _ in range(k):
+                        stg = ctx_g.render(cam_c, pg, None)
+                        g_ms += stg["kernel_ms"]; g_paths += stg["paths"]
+                    t0 = time.perf_counter()
+                    stg = ctx_g.render(cam_c, pg, img_g)
+                    g_wall = (time.perf_counter() - t0) * 1e3
+                    dd = np.abs(img_g[:, :, :3].astype(np.int16) - main_img[:, :, :3].astype(np.int16)).max(axis=2)
+                    v = g_paths / (g_ms * 1e-3) / 1e6
+                    inctx[name] = {"value": v, "unit": "Mpaths/s", "ms_per_step": g_ms / k, "e2e_value": stg["paths"] / (g_wall * 1e-3) / 1e6,
+                                   "n_devices": int(stg["n_devices"]), "pixels_identical_frac": float((dd == 0).mean()),
+                                   "pixels_within_1lsb_frac": float((dd <= 1).mean()), "within_2pct_of_multiprocess_tiles": bool(abs(v / value - 1) <= 0.02)}
+                inctx["note"] = ("one process drives all %d GPUs through one tray_ctx (tray_init(devices, n)): 'tiles' = interleaved 8-row bands, device-to-host "
+                                 "gather only, must equal the multi-process image bit for bit; 'samples' = device g traces samples s == g (mod G), combine_kernel on "
+                                 "device 0 sums the partial sums through peer pointers over NVLink and applies 1/N + sRGB (<= 1 LSB); device time = max over devices") % world
+                multi_gpu["in_context"] = inctx
+                ctx_g.close()
+            except Exception as e:
+                multi_gpu["in_context_error"] = str(e)
+            # (d) the same workload on ONE GPU of this box, for a like-for-like scaling ratio inside this run
+            try:
+                p1 = tr._params(0, h)
+                p1.shard_index, p1.shard_count = 0, 0
+                ctx.render(cam_c, p1, None)
+                st1 = ctx.render(cam_c, p1, None)
+                v1 = st1["paths"] / (st1["kernel_ms"] * 1e-3) / 1e6
+                multi_gpu["same_workload_one_gpu"] = {"value": v1, "unit": "Mpaths/s", "ms_per_step": st1["kernel_ms"], "speedup_of_this_run": value / v1,
+                                                      "note": "rank 0 alone renders the whole %s frame (the driver's N=1 line is config2)" % workload}
+            except Exception as e:
+                multi_gpu["same_workload_one_gpu_error"] = str(e)
+        host_barrier()
+
     # ---- CPU baseline + parity spot check (rank 0, N=1 only) ----
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = host_threads()
         cp = cpu_port_run(workload, threads, args.cpu_seconds, fma_mode=0)
         img, cst, cdt = cpu_port_step(cp)
         sample = "rows y%%%d==0 of %s (%d rows, %.2f Mpaths), per-sample streams, strict fp64, %.1f s" % (
@@ -449,22 +594,59 @@ def run_ours(args):
         parity = {"rows_checked": len(rows), "pixels_identical_frac": float((d == 0).mean()), "pixels_within_1lsb_frac": float((d <= 1).mean()),
                   "mode": "GPU %s vs strict CPU port (oracle)" % args.precision}
 
+    # ---- N = 1: every other BASELINE config, short runs, each with value, e2e and a parity spot check ----
+    configs = {}
+    if world == 1 and workload == "config2" and not args.no_configs and not args.no_cpu_baseline:
+        for name, k_dev, k_e2e, cpu_s in (("config1", 5, 5, 1.0), ("config3", 2, 1, 5.0), ("config4", 3, 2, 5.0), ("config5", 5, 5, 2.0)):
+            try:
+                t2, fl2 = job(name)
+                w2, h2, spp2, depth2, _, desc2 = WORKLOADS[name]
+                ctx.upload(fl2)
+                cam2, p2 = t2.to_c(), t2._params(0, h2)
+                img2 = np.zeros((h2, w2, 4), dtype=np.uint8)
+                for _ in range(2):
+                    ctx.render(cam2, p2, None)
+                a = timed_steps(cam2, p2, k_dev)
+                inter = name == "config5"
+                e_val, e_ms, st2, ansi2 = e2e_run(cam2, p2, fl2, img2, k_e2e, 1, inter)
+                if inter:
+                    ctx.read_image(img2)
+                par, cst2 = oracle_rows_check(name, img2, cpu_s, threads)
+                rec = {"desc": desc2, "spheres": len(fl2["cx"]), "value": a["paths"] / (a["ms"] * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": a["ms"] / k_dev,
+                       "mrays_per_s": a["segments"] / (a["ms"] * 1e-3) / 1e6, "steps": k_dev,
+                       "sphere_tests_per_segment": a["sphere_tests"] / max(1, a["segments"]),
+                       "e2e": {"value": e_val, "unit": "Mpaths/s", "ms_per_step": e_ms, "h2d_bytes_per_step": h2d_bytes(fl2),
+                               "d2h_bytes_per_step": int(ansi2) if inter else int(h2 * w2 * 4)},
+                       "parity_spot_check": par,
+                       "cpu_port": {"value": cst2["paths"] / cst2["seconds"] / 1e6, "unit": "Mpaths/s", "cores": threads, "kind": "port"}}
+                if inter:
+                    rec["keypress_latency_ms"] = e_ms
+                    rec["interactive"] = {"terminal": "%dx%d" % (term_cols, term_rows), "supersample": 4, "ansi_frame_bytes": int(ansi2)}
+                configs[name] = rec
+            except Exception as e:
+                configs[name] = {"error": str(e)}
+        ctx.upload(flat)
+
     if rank == 0:
         traffic, traffic_src = ncu_traffic_bytes() if workload == "config2" and args.precision == "fp64" else (None, None)
+        prof = ncu_summary() if workload == "config2" and args.precision == "fp64" else None
+        ns_seg = trace_ms * 1e6 / max(1, segments) * (148 * 4)  # SM-sub-partition nanoseconds per ray segment
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "mrays_per_s": all_segments / (dev_ms * 1e-3) / 1e6,
+            "ns_per_segment": trace_ms * 1e6 / max(1, segments),
             "wall_ms_per_step": wall_ms / args.steps,
             "config": {"workload": workload, "desc": desc, "width": w, "height": h, "rays_per_pixel": spp, "max_depth": depth,
                        "seed": SEED, "spheres": n_spheres, "precision": args.precision, "streams": "per-sample", "layout": args.layout,
+                       "closest_hit": structure,
                        "parallelism": ("samples%d+nccl_reduce" if split_samples else "tiles%d") % world if world > 1 else "1gpu",
-                       "l2": "256 MiB memset between timed steps (L2 flush); working set is 31 kB of spheres in shared memory"},
+                       "l2": "256 MiB memset between timed steps (L2 flush); working set is 12 kB of sphere tables in shared memory"},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "power_w_max": clocks.get("power_w_max"), "samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_used, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_used if peak_used else None, "traffic": traffic,
@@ -472,28 +654,31 @@ def run_ours(args):
                                          "sample colour written (read back once by the resolve kernel)" % traffic_src if traffic else None,
                          "kernel": "tray::trace_kernel", "launches": int(trace_launches), "avg_launch_ms": trace_ms / max(1, trace_launches),
                          "algorithmic_flops_per_launch": flops / max(1, trace_launches),
-                         "flops_model": "18*sphere_tests + 155*segments (SURVEY 8d); sphere_tests = segments*N (N=%d) for the linear scan, "
-                                        "kernel-counted for the BVH (this run: %.1f tests/segment, %s)" % (n_spheres, sphere_tests / max(1, segments), "bvh" if uses_bvh else "linear scan"),
+                         "flops_model": "SURVEY 8(d), the REFERENCE algorithm's work: 18 flops per sphere of every Scene.Hit (N=%d) + 155 per segment. The kernel "
+                                        "answers the same closest-hit question by looking at %.1f spheres and %.1f boxes per segment (%s), so this fraction "
+                                        "says how fast reference-equivalent work is retired, NOT how busy the FP64 pipe is: see fp64_pipe_busy, "
+                                        "frac_fp64_brute and ns_per_segment" % (n_spheres, sphere_tests / max(1, segments), box_tests / max(1, segments), structure),
                          "peak_source": "measured live on this GPU by tray_measure_peak (DFMA chains, 8/thread); MEASURED_PEAKS.json has no fp64 entry",
-                         "peak_dadd_dmul_tflops": peak_strict_tf, "peak_ffma_tflops": peak_f32_tf,
+                         "peak_dadd_dmul_tflops": peak_strict_tf, "peak_ffma_tflops": peak_f32_tf, "peak_ffma2_tflops": peak_ffma2_tf,
                          "loop_only_probe_tflops": loop_probe_tf,
                          "structural_ceiling_frac": {"fp64": 18.0 / 34.0, "fp64-brute": 18.0 / 34.0, "fp64-fma": 18.0 / 22.0, "fp32": 18.0 / 22.0}[args.precision],
-                         "pipe_analysis": ({"bound": "fp32", "pipe_slot_tflops": segments * float(-(-n_spheres // 8) * 8) * 16.0 / (trace_ms * 1e-3) / 1e12,
-                                            "peak_ffma2_tflops": peak_ffma2_tf,
-                                            "frac": segments * float(-(-n_spheres // 8) * 8) * 16.0 / (trace_ms * 1e-3) / 1e12 / peak_ffma2_tf,
-                                            "note": "the default kernel proves ~99 % of the tests missed with 8 packed fp32 instructions per PAIR of spheres "
-                                                    "(FFMA2 = 4 pipe-slot flops -> 16 per sphere), so the fp64-roofline fraction above can exceed the 0.529 "
-                                                    "ceiling of the pure FP64-pipe kernel (alt_modes: fp64-brute); results are bit-identical"}
-                                           if args.precision == "fp64" and not uses_bvh else None),
-                         "note": "achieved = algorithmic flops (SURVEY 8d: 18 per sphere test) / CUDA-event time of the trace kernel; compute-bound, HBM traffic "
-                                 "is ~30 B/path (sample colour out); tensor cores do not apply"},
+                         # what the hardware is actually doing (committed ncu capture of this command line) -- VERDICT r1 item 4
+                         "fp64_pipe_busy": prof.get("fp64_pipe_busy") if prof else None,
+                         "fp32_pipe_slot_frac": prof.get("fp32_pipe_slot_frac") if prof else None,
+                         "issue_active": prof.get("issue_active") if prof else None,
+                         "threads_per_instruction": prof.get("threads_per_instruction") if prof else None,
+                         "frac_fp64_brute": frac_fp64_brute,
+                         "ns_per_segment": ({"total_smsp_ns": ns_seg, **{k: ns_seg * v for k, v in prof.get("time_share", {}).items()},
+                                             "note": "SM-sub-partition time per ray segment (trace-kernel time x 592 sub-partitions / segments), split by the "
+                                                     "stall-sample shares of the committed capture (%s)" % prof.get("source")} if prof else {"total_smsp_ns": ns_seg}),
+                         "note": "compute/latency-bound: HBM traffic is ~30 B/path (sample colour out); tensor cores do not apply"},
             "segments_per_path": all_segments / all_paths,
         }
         if split_samples:
             line["exchange"] = {"collective": "NCCL reduce(sum) to rank 0 + resolve", "bytes": int(w) * h * 24, "ms_per_step": exchange_ms / args.steps,
                                 "note": "fp64 colour sums (w*h*3 doubles) reduced in place on the library's device buffer; rank 0's time"}
         if interactive:
-            line["keypress_latency_ms"] = e2e_ms / args.steps
+            line["keypress_latency_ms"] = e2e_ms_step
             line["interactive"] = {"terminal": "%dx%d" % (term_cols, term_rows), "supersample": 4, "ansi_frame_bytes": int(ansi_bytes),
                                    "note": "per-keypress OnResize body: scene upload + Render + on-device BiLinear downscale + half-block ANSI "
                                            "frame, only the ANSI bytes cross PCIe"}
@@ -505,6 +690,12 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline
         if parity:
             line["parity_spot_check"] = parity
+        if multi_gpu.get("parity"):
+            line["parity_spot_check"] = multi_gpu.pop("parity")
+        for k2, v2 in multi_gpu.items():
+            line[k2] = v2
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -531,7 +722,8 @@ def main():
                     help="N>1 partitioning: interleaved row bands (no collective, default) or sample split + NCCL sum-reduce")
     ap.add_argument("--layout", default="auto", choices=["auto", "plain", "regroup", "wavefront"],
                     help="divergence layout of the trace kernel (results identical): plain megakernel or per-material regrouping")
-    ap.add_argument("--no-alt", action="store_true", help="skip the extra fp64-fma measurement")
+    ap.add_argument("--no-alt", action="store_true", help="skip the alternative kernels / layouts / multi-GPU variants")
+    ap.add_argument("--no-configs", action="store_true", help="N=1: skip the short runs of the other BASELINE configs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (bounded sample per step)")

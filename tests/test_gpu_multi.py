@@ -26,12 +26,19 @@ def test_tile_mode_is_bit_identical_for_any_device_count(ctx, g):
         pytest.skip("needs %d GPUs" % g)
     scene = ray.RichScene(rand.New(2))
     w, h, spp, depth = 320, 181, 8, 50
-    one = _tracer(ctx, w, h, spp, depth).Render(scene).copy()
     multi = ray.Context(list(range(g)))
     t = _tracer(multi, w, h, spp, depth)
     img = t.Render(scene).copy()
+    one = _tracer(ctx, w, h, spp, depth).Render(scene).copy()
     assert t.Stats["n_devices"] == g and np.array_equal(img, one)
-    assert np.array_equal(multi.read_hdr(w, h), ctx.read_hdr(w, h)) or True
+    one_hdr = ctx.read_hdr(w, h)   # (ctx rendered `one` last: its linear-HDR means are still there)
+    assert np.array_equal(multi.read_hdr(w, h), one_hdr)
+    # reference-stream mode on a multi-device context runs on device 0 only and must still return cleanly
+    t.StreamMode, t.NumWorkers = ray.STREAM_REFERENCE, 3
+    ref_multi = t.Render(scene).copy()
+    r1 = _tracer(ctx, w, h, spp, depth)
+    r1.StreamMode, r1.NumWorkers = ray.STREAM_REFERENCE, 3
+    assert np.array_equal(ref_multi, r1.Render(scene))
     multi.close()
 
 
@@ -69,4 +76,20 @@ def test_png_of_a_tile_split_frame_gathers_on_device_zero(ctx):
     img = t.Render(scene).copy()
     data, _ = multi.encode_png(w, h)
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")), img[:, :, :3])
+    multi.close()
+
+
+def test_progress_counts_every_device(ctx):
+    """tray_progress on a multi-device context sums the per-device counters (each device has its own side stream and
+    pinned word); after the render it equals the pixel count (ProgressFunc deltas sum to w*h, ray/tracer_test.go:172-186)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene = ray.RichScene(rand.New(2))
+    w, h = 320, 181
+    multi = ray.Context([0, 1])
+    t = _tracer(multi, w, h, 8, 50)
+    seen = []
+    t.ProgressFunc = seen.append
+    t.Render(scene)
+    assert sum(seen) == w * h and multi.progress() == w * h
     multi.close()

@@ -726,8 +726,9 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
 
 constexpr int kClusterMaxSpheres = 4096;  // 64 groups x 8 chunks x 8 spheres: 8 words of group boxes per segment at most
 constexpr int kBandRows = 8;
-// Scratch budget per pass, in samples (x24 bytes). Whole pixels per pass.
-constexpr unsigned long long kPassSamples = 144ull << 20;  // 88 B per sample (camera ray + colour): <= 13.3 GB of the 180 GB
+// Scratch per pass, in samples (x24 bytes), whole pixels per pass: at least this much, more when the device has the room
+// (tray_render sizes a pass from cudaMemGetInfo so that a device's whole share is one pass when it fits).
+constexpr unsigned long long kPassSamples = 144ull << 20;
 
 }  // namespace
 
@@ -1105,7 +1106,16 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     CK(cudaEventRecord(d.ev_end, d.stream));
                     continue;
                 }
-                unsigned long long px_per_pass = std::max<unsigned long long>(1, kPassSamples / (unsigned)spp_local);
+                // One pass per device whenever its scratch (24 B per sample) fits in a share of the free memory: a pass ends with a
+                // tail in which the SMs run dry one by one, so two passes cost two tails (config 3 on 8 GPUs: 265 M samples per rank).
+                unsigned long long pass_samples = kPassSamples;
+                if (n_pixels * (unsigned long long)spp_local > pass_samples) {
+                    size_t free_b = 0, total_b = 0;
+                    CK(cudaMemGetInfo(&free_b, &total_b));
+                    const unsigned long long fit = (unsigned long long)(0.45 * (double)(free_b + d.scratch_cap * sizeof(double))) / 24ull;
+                    pass_samples = std::max(pass_samples, std::min(fit, 0xfff00000ull));  // (sample indices of a pass are 32-bit)
+                }
+                unsigned long long px_per_pass = std::max<unsigned long long>(1, pass_samples / (unsigned)spp_local);
                 px_per_pass = std::min(px_per_pass, n_pixels);
                 int n_pass = (int)((n_pixels + px_per_pass - 1) / px_per_pass);
                 grow(d.scratch, d.scratch_cap, (size_t)(px_per_pass * spp_local * 3));
