@@ -150,20 +150,16 @@ def cpu_port_step(cp):
     return img, st, dt
 
 
-def oracle_rows_check(workload, host_img, target_seconds, threads, rate_hint=None):
-    """Parity spot check: a bounded set of rows y == off (mod step) of `workload` rendered by the CPU oracle (strict fp64,
-    per-sample streams) and compared with the same rows of the GPU image. Returns (parity dict, cpu stats)."""
+def oracle_rows_check(workload, host_img, n_rows, threads):
+    """Parity spot check: `n_rows` rows spread over the image (y == off mod step) of `workload` rendered by the CPU oracle
+    (strict fp64, per-sample streams, one row per host thread at a time) and compared with the same rows of the GPU image.
+    Returns (parity dict, cpu stats)."""
     from oracle import oracle as O
     w, h, spp, depth, half, _ = WORKLOADS[workload]
     scene = O.rich_scene(SEED, half)
     cam = O.camera_init(w, h, **O.RICH_CAMERA)
     p = O.make_params(w, h, spp=spp, max_depth=depth, seed=SEED, num_workers=threads, stream_mode=1, fma_mode=0)
-    if rate_hint is None:  # calibrate on one row in the middle of the image
-        t0 = time.perf_counter()
-        _, st = O.render_sampled_rows(scene, cam, p, h, h // 2, threads)
-        rate_hint = st["paths"] / max(time.perf_counter() - t0, 1e-6)
-    rows = int(max(1, min(h, target_seconds * rate_hint / (w * spp))))
-    step = max(1, h // rows)
+    step = max(1, h // max(1, min(h, n_rows)))
     off = step // 2
     t0 = time.perf_counter()
     img, st = O.render_sampled_rows(scene, cam, p, step, off, threads)
@@ -535,7 +531,7 @@ def run_ours(args):
         if rank == 0:
             # (a) config-size parity: strided rows of the multi-process image against the CPU oracle
             try:
-                multi_gpu["parity"], _ = oracle_rows_check(workload, main_img, 6.0, threads)
+                multi_gpu["parity"], _ = oracle_rows_check(workload, main_img, threads, threads)  # one row per host thread: ~1 Mpaths each at config 3
             except Exception as e:
                 multi_gpu["parity_error"] = str(e)
             # (b) ONE process, ONE context over all N devices: what the cgo shim's TRAY_GPUS uses (Tracer.Render's fan-out,
@@ -597,7 +593,7 @@ def run_ours(args):
     # ---- N = 1: every other BASELINE config, short runs, each with value, e2e and a parity spot check ----
     configs = {}
     if world == 1 and workload == "config2" and not args.no_configs and not args.no_cpu_baseline:
-        for name, k_dev, k_e2e, cpu_s in (("config1", 5, 5, 1.0), ("config3", 2, 1, 5.0), ("config4", 3, 2, 5.0), ("config5", 5, 5, 2.0)):
+        for name, k_dev, k_e2e, n_rows in (("config1", 5, 5, 45), ("config3", 2, 1, threads), ("config4", 3, 2, max(1, threads // 2)), ("config5", 5, 5, 45)):
             try:
                 t2, fl2 = job(name)
                 w2, h2, spp2, depth2, _, desc2 = WORKLOADS[name]
@@ -611,7 +607,7 @@ def run_ours(args):
                 e_val, e_ms, st2, ansi2 = e2e_run(cam2, p2, fl2, img2, k_e2e, 1, inter)
                 if inter:
                     ctx.read_image(img2)
-                par, cst2 = oracle_rows_check(name, img2, cpu_s, threads)
+                par, cst2 = oracle_rows_check(name, img2, n_rows, threads)
                 rec = {"desc": desc2, "spheres": len(fl2["cx"]), "value": a["paths"] / (a["ms"] * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": a["ms"] / k_dev,
                        "mrays_per_s": a["segments"] / (a["ms"] * 1e-3) / 1e6, "steps": k_dev,
                        "sphere_tests_per_segment": a["sphere_tests"] / max(1, a["segments"]),
