@@ -130,8 +130,8 @@ def test_rich_scene_layout():
 
 def box_ray_constants(o, d, cl_r):
     a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
-    inv_n = 1.0 / math.sqrt(a)
-    fd = [F32(d[k] * inv_n) for k in range(3)]
+    ln = math.sqrt(a)                                   # Unit(D) of the RayColor step (ray/vec3.go:117-120), fp64
+    fd = [F32(d[k] / ln) for k in range(3)]
     lim = F32(8.6736174e-19)
     inv = []
     for k in range(3):

@@ -1155,7 +1155,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     R.scratch = d.scratch; R.n_pixels = npx; R.pass_pixel0 = p0; R.spp_local = spp_local;
                     R.inv_spp = 1.0 / (double)p->spp; R.partial = subset ? p->sums_mode : (split_samples ? 1 : 0);
                     R.rgba = d.rgba; R.hdr = d.hdr; R.srgb_thr = d.srgb_thr;
-                    resolve_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, d.stream>>>(R);
+                    resolve_kernel<<<(unsigned)((3 * npx + 255) / 256), 256, 0, d.stream>>>(R);
                     CK(cudaGetLastError());
                     launches += 2;
                 }

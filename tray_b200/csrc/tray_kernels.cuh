@@ -418,13 +418,13 @@ __device__ __noinline__ BestHit<T> flush_candidates_lex(const typename Vec4T<T>:
 // cannot report a miss. tests/test_cluster_box_model.py replays the test in exact single-rounded arithmetic.
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4* sblob, const typename Vec4T<T>::type* __restrict__ ggeo,
-                                             uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a,
+                                             uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a, T udx, T udy, T udz,
                                              T& best_t, int& best, int& ncand, unsigned& nchunks, unsigned& nboxes,
                                              const volatile double* parked = nullptr) {
-    // ---- per-ray constants of the pair pre-filter (same derivation as filter_scan) ----
+    // ---- per-ray constants of the pair pre-filter (as filter_scan; the unit direction is Unit(D) of the RayColor step,
+    //      computed by the caller in fp64 with IEEE sqrt and divisions: within 2 ulp of D/|D|, far inside the bounds) ----
     const float u32 = 5.9604645e-8f;
-    const double inv_n = div_f64(1.0, sqrt_f64((double)a));
-    const double ddx = (double)dx * inv_n, ddy = (double)dy * inv_n, ddz = (double)dz * inv_n;
+    const double ddx = (double)udx, ddy = (double)udy, ddz = (double)udz;
     const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
     float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
     const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
@@ -568,8 +568,15 @@ struct RegroupBuf {
 // that the divergent tail of the iteration (scatter, generators, unwind, regeneration) runs on warps that are mostly of
 // one kind. Paths have no lane affinity; the attenuation stack lives in global memory under a slot id that travels with
 // the path. Results are bit-identical to the plain layout (pure data movement).
+// Register budget of the trace kernel: resident CTAs per SM (MINB), or -- tuning builds -- an explicit register count
+// (TRAY_MAXNREG; e.g. 112 registers x 96 threads x 6 CTAs = 18 warps per SM, which no whole CTA count of 128 threads gives).
+#ifdef TRAY_MAXNREG
+#define TRAY_TRACE_BOUNDS(TPB, MINB) __maxnreg__(TRAY_MAXNREG)
+#else
+#define TRAY_TRACE_BOUNDS(TPB, MINB) __launch_bounds__(TPB, MINB)
+#endif
 template <typename T, bool FMA, int TPB, int MINB, int GEO, bool REGROUP = false>
-__global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
+__global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
                                                           const __grid_constant__ GeoArg<T, GEO> GP) {
     typedef typename Vec4T<T>::type T4;
     constexpr int CH = TRAY_CH;  // spheres per candidate-mask chunk (n_pad is a multiple of 8)
@@ -686,11 +693,12 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
         // ---------------- Scene.Hit: brute force over all spheres ----------------
         T best_t = t_inf<T>();
         int best = -1;
+        V3<T> ud = mk<T>(T(0), T(1), T(0));
         if (warp_alive) {  // (regroup layout: warps left without a path near the end of a pass skip the scan)
 #if TRAY_PARK_STATE
         // Park what the scan does not need (fp64 ray, generator, counters of the path) in shared memory, so that the loop's
         // registers are not shared with ~20 registers of path state.
-        __shared__ double s_park[8][TPB];
+        __shared__ double s_park[11][TPB];
         __shared__ int s_parki[3][TPB];
         volatile double* pk = &s_park[0][tid];
         volatile int* pki = &s_parki[0][tid];
@@ -701,6 +709,12 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             pk[6 * TPB] = __longlong_as_double((long long)rng.hi); pk[7 * TPB] = __longlong_as_double((long long)rng.lo);
             pki[0] = depth_left; pki[TPB] = sp; pki[2 * TPB] = (int)my_li;
         }
+#endif
+        // Unit(r.Direction) is needed by the sky (objects.go:69), Metal (materials.go:29) and Dielectric (materials.go:52): computed
+        // once for every lane, and BEFORE the scan, whose fp32 filters take their normalised direction from it.
+        ud = unit(D);
+#if TRAY_PARK_STATE
+        if constexpr (kPark) { pk[8 * TPB] = (double)ud.x; pk[9 * TPB] = (double)ud.y; pk[10 * TPB] = (double)ud.z; }
 #endif
         T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
         T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
@@ -714,7 +728,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             (void)nchunks; (void)nboxes;
 #if TRAY_PARK_STATE
             if constexpr (kPark) {
-                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, nchunks, nboxes, pk);
+                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pk);
                 else
                 filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pk);
                 ox = T(pk[0]); oy = T(pk[TPB]); oz = T(pk[2 * TPB]); dx = T(pk[3 * TPB]); dy = T(pk[4 * TPB]); dz = T(pk[5 * TPB]);
@@ -722,10 +736,11 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
                 O = mk<T>(ox, oy, oz); D = mk<T>(dx, dy, dz);
                 rng.hi = (uint64_t)__double_as_longlong(pk[6 * TPB]); rng.lo = (uint64_t)__double_as_longlong(pk[7 * TPB]);
                 depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
+                ud = mk<T>(T(pk[8 * TPB]), T(pk[9 * TPB]), T(pk[10 * TPB]));
             } else
 #endif
             {
-                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, nchunks, nboxes);
+                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes);
                 else filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
             }
             if constexpr (GEO == kGeoCluster) {
@@ -812,9 +827,7 @@ __global__ void __launch_bounds__(TPB, MINB) trace_kernel(const __grid_constant_
             nseg++;
             bool finish = false;
             V3<T> col = mk<T>(T(0), T(0), T(0));
-            // Unit(r.Direction) is needed by the sky (objects.go:69), Metal (materials.go:29) and Dielectric
-            // (materials.go:52): computed once for every lane instead of inside three divergent branches.
-            const V3<T> ud = unit(D);
+            if constexpr (REGROUP) ud = unit(D);  // (the exchange moved the path to another lane; Unit(D) is not part of the exchanged state)
             if (best < 0) {
                 T ab = T(0.5) * (ud.y + T(1));  // AmbientLight.Hit, objects.go:68-73
                 col = mk<T>(T(S.bg_a[0]), T(S.bg_a[1]), T(S.bg_a[2])) * (T(1) - ab) + mk<T>(T(S.bg_b[0]), T(S.bg_b[1]), T(S.bg_b[2])) * ab;
@@ -913,29 +926,23 @@ struct ResolveArgs {
 };
 
 __global__ void __launch_bounds__(256) resolve_kernel(const ResolveArgs R) {
-    unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (pixel, channel): three times the loads in flight of a thread per pixel, neighbouring threads read
+    // neighbouring doubles (the kernel is HBM-bound: 24 B per sample read once)
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long p = t / 3ull;
+    const int c = (int)(t - p * 3ull);
     if (p >= R.n_pixels) return;
-    const double* s = R.scratch + 3ull * p * (unsigned)R.spp_local;
-    unsigned long long lp = R.pass_pixel0 + p;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    if (R.partial == 2) { sx = R.hdr[3 * lp]; sy = R.hdr[3 * lp + 1]; sz = R.hdr[3 * lp + 2]; }  // progressive: same running sum
-    for (int j = 0; j < R.spp_local; j++) {  // colorSum = Add(colorSum, color), sample order
-        sx = sx + s[3 * j];
-        sy = sy + s[3 * j + 1];
-        sz = sz + s[3 * j + 2];
-    }
-    if (R.partial) {
-        R.hdr[3 * lp] = sx; R.hdr[3 * lp + 1] = sy; R.hdr[3 * lp + 2] = sz;
-        return;
-    }
-    double cx = sx * R.inv_spp, cy = sy * R.inv_spp, cz = sz * R.inv_spp;  // SMul(colorSum, colorSumDiv)
-    if (R.hdr) { R.hdr[3 * lp] = cx; R.hdr[3 * lp + 1] = cy; R.hdr[3 * lp + 2] = cz; }
-    uchar4 px;
-    px.x = linear_to_srgb(R.srgb_thr, cx);
-    px.y = linear_to_srgb(R.srgb_thr, cy);
-    px.z = linear_to_srgb(R.srgb_thr, cz);
-    px.w = 255;
-    reinterpret_cast<uchar4*>(R.rgba)[lp] = px;
+    const double* s = R.scratch + 3ull * p * (unsigned)R.spp_local + c;
+    const unsigned long long lp = R.pass_pixel0 + p;
+    double sum = 0.0;
+    if (R.partial == 2) sum = R.hdr[3 * lp + c];  // progressive: same running sum
+#pragma unroll 8
+    for (int j = 0; j < R.spp_local; j++) sum = sum + s[3 * j];  // colorSum = Add(colorSum, color), sample order (ray/tracer.go:143)
+    if (R.partial) { R.hdr[3 * lp + c] = sum; return; }
+    const double v = sum * R.inv_spp;  // SMul(colorSum, colorSumDiv)
+    if (R.hdr) R.hdr[3 * lp + c] = v;
+    R.rgba[4 * lp + c] = linear_to_srgb(R.srgb_thr, v);
+    if (c == 0) R.rgba[4 * lp + 3] = 255;
 }
 
 // MaxDepth == 0: RayColor returns black for every sample (ray/objects.go:50-52), the pixel is (0,0,0,255).
