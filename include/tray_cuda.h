@@ -174,6 +174,14 @@ TRAY_API int tray_abi_version(void);
 #define TRAY_BVH_BUILD_AUTO 0
 #define TRAY_BVH_BUILD_HOST 1
 #define TRAY_BVH_BUILD_DEVICE 2
+/* TRAY_CFG_INDISC / TRAY_CFG_UNITVEC: which body of fortio.org/rand's Rand.InDisc / Rand.UnitVector the device generators use.
+ * Those bodies are not in the reference tree and no reference test pins their values (call sites ray/tracer.go:138,
+ * ray/camera.go:128, ray/rand.go:31); 0 = the default restatement, the others are the candidate bodies the oracle also knows
+ * (oracle_set_variants): InDisc 1 = polar (angle from the 1st uniform, radius sqrt of the 2nd), 2 = polar the other way round;
+ * UnitVector 1 = rejection in the cube (ray/rand.go:50-58), 2 = spherical angles (ray/rand.go:62-69). Every variant is bit-exact
+ * against the oracle's; once real Go vectors are available (tools/go_vectors) the matching body is a flag. */
+#define TRAY_CFG_INDISC 2
+#define TRAY_CFG_UNITVEC 3
 TRAY_API int tray_configure(tray_ctx *ctx, int32_t key, int64_t value);
 TRAY_API int64_t tray_query(tray_ctx *ctx, int32_t key);
 

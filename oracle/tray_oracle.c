@@ -130,6 +130,53 @@ static double go_tan(double x) {
     return y;
 }
 
+/* Go math.Sin / math.Cos, pure-Go Cephes forms (src/math/sin.go; no assembly on amd64 / arm64), arguments below
+ * the Payne-Hanek threshold (the variants below call them with angles in [0, 2*Pi)). Only + - * and exact
+ * conversions, so the device restatement (tray_device.cuh) agrees bit for bit. */
+static const double GO_SIN[6] = {1.58962301576546568060e-10, -2.50507477628578072866e-8, 2.75573136213857245213e-6,
+                                 -1.98412698295895385996e-4, 8.33333333332211858878e-3, -1.66666666666666307295e-1};
+static const double GO_COS[6] = {-1.13585365213876817300e-11, 2.08757008419747316778e-9, -2.75573141792967388112e-7,
+                                 2.48015872888517045348e-5, -1.38888888888730564116e-3, 4.16666666666665929218e-2};
+static double go_sincos_reduce(double x, uint64_t *jo) {
+    const double PI4A = 7.85398125648498535156e-1, PI4B = 3.77489470793079817668e-8,
+                 PI4C = 2.69515142907905952645e-15;
+    uint64_t j = (uint64_t)(x * (4 / M_PI));
+    double y = (double)j;
+    if (j & 1) { j++; y++; }
+    *jo = j & 7;
+    return ((x - y * PI4A) - y * PI4B) - y * PI4C;
+}
+static double go_sin_poly(double z, double zz) {
+    return z + z * zz * ((((((GO_SIN[0] * zz) + GO_SIN[1]) * zz + GO_SIN[2]) * zz + GO_SIN[3]) * zz + GO_SIN[4]) * zz + GO_SIN[5]);
+}
+static double go_cos_poly(double zz) {
+    return 1.0 - 0.5 * zz + zz * zz * ((((((GO_COS[0] * zz) + GO_COS[1]) * zz + GO_COS[2]) * zz + GO_COS[3]) * zz + GO_COS[4]) * zz + GO_COS[5]);
+}
+static double go_sin(double x) {
+    int sign = 0;
+    if (x == 0 || isnan(x)) return x;
+    if (isinf(x)) return NAN;
+    if (x < 0) { x = -x; sign = 1; }
+    uint64_t j;
+    double z = go_sincos_reduce(x, &j);
+    if (j > 3) { sign = !sign; j -= 4; }
+    double zz = z * z;
+    double y = (j == 1 || j == 2) ? go_cos_poly(zz) : go_sin_poly(z, zz);
+    return sign ? -y : y;
+}
+static double go_cos(double x) {
+    int sign = 0;
+    if (isnan(x) || isinf(x)) return NAN;
+    x = fabs(x);
+    uint64_t j;
+    double z = go_sincos_reduce(x, &j);
+    if (j > 3) { j -= 4; sign = !sign; }
+    if (j > 1) sign = !sign;
+    double zz = z * z;
+    double y = (j == 1 || j == 2) ? go_sin_poly(z, zz) : go_cos_poly(zz);
+    return sign ? -y : y;
+}
+
 /* ------------------------------------------------------------------ */
 /* RNG: Go math/rand/v2 PCG-DXSM + fortio.org/rand wrappers              */
 /* ------------------------------------------------------------------ */
@@ -216,7 +263,7 @@ static void rng_unit_vector(rng_t *r, double *ox, double *oy, double *oz) {
         double angle = rng_f64(r) * 2 * M_PI;
         double z = rng_f64(r) * 2 - 1;
         double rad = sqrt(1 - z * z);
-        *ox = rad * cos(angle); *oy = rad * sin(angle); *oz = z;
+        *ox = rad * go_cos(angle); *oy = rad * go_sin(angle); *oz = z;
         return;
     }
     for (;;) {
@@ -234,7 +281,7 @@ static void rng_in_disc(rng_t *r, double radius, double *ox, double *oy) {
         double u1 = rng_f64(r), u2 = rng_f64(r);
         double ang = (g_indisc_variant == 1 ? u1 : u2) * 2 * M_PI;
         double rr = radius * sqrt(g_indisc_variant == 1 ? u2 : u1);
-        *ox = rr * cos(ang); *oy = rr * sin(ang);
+        *ox = rr * go_cos(ang); *oy = rr * go_sin(ang);
         return;
     }
     for (;;) {
@@ -819,6 +866,8 @@ EXPORT void oracle_rng_in_disc(uint64_t idx, uint64_t seed, double radius, int n
 }
 EXPORT double oracle_go_log(double x) { return go_log(x); }
 EXPORT double oracle_go_exp(double x) { return go_exp(x); }
+EXPORT double oracle_go_sin(double x) { return go_sin(x); }
+EXPORT double oracle_go_cos(double x) { return go_cos(x); }
 EXPORT double oracle_go_tan(double x) { return go_tan(x); }
 
 /* Single-object / single-op probes so the reference's unit-test tables

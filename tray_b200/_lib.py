@@ -16,6 +16,7 @@ ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH, ACCEL_CLUSTER = 0, 1, 2, 3
 SUMS_OFF, SUMS_OVERWRITE, SUMS_ACCUMULATE = 0, 1, 2
 LAYOUT_AUTO, LAYOUT_PLAIN, LAYOUT_REGROUP, LAYOUT_WAVEFRONT = 0, 1, 2, 3
 CFG_BVH_BUILD, BVH_BUILD_AUTO, BVH_BUILD_HOST, BVH_BUILD_DEVICE = 1, 0, 1, 2
+CFG_INDISC, CFG_UNITVEC = 2, 3
 
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",

@@ -204,6 +204,7 @@ struct tray_ctx {
     int bvh_build = TRAY_BVH_BUILD_AUTO;  // tray_configure(TRAY_CFG_BVH_BUILD)
     int bvh_built_on_device = 0;          // what the last upload did (tray_query)
     int cluster_unfilterable = 0;         // spheres of the scene the fp32 filter cannot bound (every ray tests them exactly)
+    int indisc_variant = 0, unitvec_variant = 0;  // tray_configure(TRAY_CFG_INDISC / TRAY_CFG_UNITVEC)
     bool hdr_is_sums = false;          // last render left raw colour sums (sums_mode != 0)
     uint64_t sums_samples = 0;         // samples per pixel accumulated in them
     int sums_key[6] = {0, 0, 0, 0, 0, 0};  // geometry the sums belong to (w, h, y0, y1, shard_index, shard_count)
@@ -243,6 +244,7 @@ template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
     fill_cluster(s, d);
+    s.unitvec_variant = ctx->unitvec_variant;
     s.bvh = d.bvh_present ? d.bvh : nullptr; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
@@ -252,13 +254,15 @@ template <> DevScene<float> dev_scene<float>(const tray_ctx* ctx, const Device& 
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_f; s.radius = d.radius_f; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
     fill_cluster(s, d);
+    s.unitvec_variant = ctx->unitvec_variant;
     s.bvh = nullptr; s.bvh_leaf_ids = nullptr; s.bvh_always = nullptr; s.bvh_n_always = 0; s.bvh_extent = 0;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
     return s;
 }
 
-DevCamera dev_camera(const tray_camera* c) {
+DevCamera dev_camera(const tray_camera* c, int indisc_variant = 0) {
     DevCamera d;
+    d.indisc_variant = indisc_variant;
     for (int i = 0; i < 3; i++) {
         d.pos[i] = c->position[i]; d.p00[i] = c->pixel00[i]; d.px[i] = c->pixel_x[i]; d.py[i] = c->pixel_y[i];
         d.du[i] = c->defocus_u[i]; d.dv[i] = c->defocus_v[i];
@@ -1003,7 +1007,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->have_image = false; ctx->have_hdr = false;
         ctx->progress_base = 0; ctx->progress_spp = p->spp; ctx->rendering = true;
         for (Device& d : ctx->devs) { d.local_rows.clear(); d.passes = 0; d.ev_used = 0; d.timed = false; }
-        DevCamera dcam = dev_camera(cam);
+        DevCamera dcam = dev_camera(cam, ctx->indisc_variant);
         const int ext_count = p->shard_count > 1 ? p->shard_count : 1;
         const int ext_index = p->shard_count > 1 ? p->shard_index : 0;
         if (ext_index < 0 || ext_index >= ext_count) throw std::runtime_error("tray_render: shard_index out of range");
@@ -1311,6 +1315,8 @@ int tray_configure(tray_ctx* ctx, int32_t key, int64_t value) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (key == TRAY_CFG_BVH_BUILD && value >= TRAY_BVH_BUILD_AUTO && value <= TRAY_BVH_BUILD_DEVICE) { ctx->bvh_build = (int)value; return TRAY_OK; }
+    if (key == TRAY_CFG_INDISC && value >= 0 && value <= 2) { ctx->indisc_variant = (int)value; return TRAY_OK; }
+    if (key == TRAY_CFG_UNITVEC && value >= 0 && value <= 2) { ctx->unitvec_variant = (int)value; return TRAY_OK; }
     return fail(ctx, TRAY_E_INVALID, "tray_configure: unknown key or value");
 }
 
@@ -1318,6 +1324,8 @@ int64_t tray_query(tray_ctx* ctx, int32_t key) {
     if (!ctx) return -1;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (key == TRAY_CFG_BVH_BUILD) return ctx->bvh_built_on_device;
+    if (key == TRAY_CFG_INDISC) return ctx->indisc_variant;
+    if (key == TRAY_CFG_UNITVEC) return ctx->unitvec_variant;
     return -1;
 }
 
@@ -1393,7 +1401,7 @@ int tray_rng_dump(tray_ctx* ctx, int32_t kind, uint64_t idx, uint64_t seed, doub
         int per = kind == 3 ? 3 : (kind == 4 ? 2 : 1);
         DevTmp tmp(sizeof(double) * n * per);
         double* dout = tmp.as<double>();
-        rng_dump_kernel<<<1, 128, 0, d.stream>>>(kind, idx, seed, radius, n, dout);
+        rng_dump_kernel<<<1, 128, 0, d.stream>>>(kind, idx, seed, radius, n, dout, ctx->indisc_variant, ctx->unitvec_variant);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(d.stream));
         CK(cudaMemcpy(out, dout, sizeof(double) * n * per, cudaMemcpyDeviceToHost));

@@ -76,7 +76,7 @@ __device__ __forceinline__ void camera_sample(const TraceArgs& A, unsigned my_li
     unsigned long long idx = ((unsigned long long)y * (unsigned)A.width + (unsigned)x) * (unsigned)A.spp + (unsigned)s;
     rng = pcg_new_idx(idx, A.seed);
     double jx = 0.0, jy = 0.0;
-    if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);  // ray/tracer.go:136-139
+    if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy, A.cam.indisc_variant);  // ray/tracer.go:136-139
     get_ray(A.cam, rng, (double)x, (double)y, jx, jy, o64, d64);
 }
 
@@ -457,8 +457,9 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     auto lds4 = [](float4& v, unsigned addr) {
         asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     };
-    unsigned mask = 0;
-    auto pair = [&](const float4& g0, const float4& g1) {  // two spheres: 8 packed instructions (see filter_scan)
+    // Every pair of tests yields its own 2-bit word and the four words of a chunk are merged by a tree, so that the bit
+    // gathering is a dependency chain of 4 instructions instead of 8 funnel shifts in a row (the scan is latency-bound).
+    auto pair = [&](const float4& g0, const float4& g1) -> unsigned {  // two spheres: 8 packed instructions (see filter_scan)
         const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
         float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
         float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);
@@ -466,10 +467,10 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
         float2 v1 = __ffma2_rn(h, h, nc);
         int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
         int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
-        mask = __funnelshift_l((unsigned)mx, mask, 1);
-        mask = __funnelshift_l((unsigned)my, mask, 1);
+        return __funnelshift_l((unsigned)my, (unsigned)mx >> 31, 1);   // bit 1: first sphere missed, bit 0: second
     };
-    auto boxes = [&](unsigned addr) {  // two boxes: 12 packed instructions + 2 x (2 FMNMX3 + FADD + LOP3 + SHF)
+    auto merge4 = [](unsigned p0, unsigned p1, unsigned p2, unsigned p3) -> unsigned { return (((p0 << 2) | p1) << 4) | ((p2 << 2) | p3); };
+    auto boxes = [&](unsigned addr) -> unsigned {  // two boxes: 12 packed instructions + 2 x (2 FMNMX3 + FADD + LOP3 + SHF)
         float4 b0, b1, b2;
         lds4(b0, addr); lds4(b1, addr + 16); lds4(b2, addr + 32);
         const float2 ax = __ffma2_rn(make_float2(b0.x, b0.y), IX, NQX), ay = __ffma2_rn(make_float2(b0.z, b0.w), IY, NQY),
@@ -481,10 +482,10 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
         const float2 fx = __fadd2_rn(ax, bx), fy = __fadd2_rn(ay, by), fz = __fadd2_rn(az, bz);
         const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tf0 = fminf(fminf(fx.x, fy.x), fz.x);
         const float tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y), tf1 = fminf(fminf(fx.y, fy.y), fz.y);
-        mask = __funnelshift_l((unsigned)(__float_as_int(tf0 - tn0) | __float_as_int(tf0)), mask, 1);
-        mask = __funnelshift_l((unsigned)(__float_as_int(tf1 - tn1) | __float_as_int(tf1)), mask, 1);
+        return __funnelshift_l((unsigned)(__float_as_int(tf1 - tn1) | __float_as_int(tf1)),
+                               (unsigned)(__float_as_int(tf0 - tn0) | __float_as_int(tf0)) >> 31, 1);
     };
-    auto may_hit8 = [&]() -> unsigned {  // the 8 bits just shifted in -> this lane's "may hit" byte, then the warp's union
+    auto may_hit8 = [&](unsigned mask) -> unsigned {  // 8 "missed" bits -> this lane's "may hit" byte, then the warp's union
         unsigned hit = off ? 0xffu : (~mask & 0xffu);
         if (!has) hit = 0u;
         return __reduce_or_sync(kFull, hit);
@@ -512,8 +513,7 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                 float4 a0, a1, a2, a3, b0, b1, b2, b3;
                 lds4(a0, ad); lds4(a1, ad + 16); lds4(a2, ad + 32); lds4(a3, ad + 48);
                 lds4(b0, ad + 64); lds4(b1, ad + 80); lds4(b2, ad + 96); lds4(b3, ad + 112);
-                mask = 0;
-                pair(a0, a1); pair(a2, a3); pair(b0, b1); pair(b2, b3);
+                const unsigned mask = merge4(pair(a0, a1), pair(a2, a3), pair(b0, b1), pair(b2, b3));
                 nchunks++;
                 unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
                 if (m) {
@@ -545,9 +545,7 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                 g = w * 8 + 7 - gbit;
                 ad = a_box2 + (unsigned)g * (4u * 48u);
             }
-            mask = 0;
-            boxes(ad); boxes(ad + 48); boxes(ad + 96); boxes(ad + 144);
-            const unsigned u8 = may_hit8();
+            const unsigned u8 = may_hit8(merge4(boxes(ad), boxes(ad + 48), boxes(ad + 96), boxes(ad + 144)));
             nboxes += 8;
             if (!word_done) { ug = u8; word_done = true; } else uc = u8;
         }
@@ -842,7 +840,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 // one shared UnitVector draw site for Lambertian (always) and Metal (iff Fuzz > 0)
                 const bool need_uv = kind == 0 || (kind == 1 && prm.w > 0.0);
                 V3<T> uv = mk<T>(T(0), T(0), T(0));
-                if (need_uv) { V3<double> u64 = pcg_unit_vector(rng, zig); uv = mk<T>(T(u64.x), T(u64.y), T(u64.z)); }
+                if (need_uv) { V3<double> u64 = pcg_unit_vector(rng, zig, S.unitvec_variant); uv = mk<T>(T(u64.x), T(u64.y), T(u64.z)); }
                 bool scattered = true;
                 V3<T> D2;
                 if (kind == 0) {  // Lambertian.Scatter, materials.go:13-21
@@ -1025,7 +1023,7 @@ __global__ void __launch_bounds__(32) reference_stream_kernel(const RefArgs A, c
             V3<double> sum = mk<double>(0.0, 0.0, 0.0);
             for (int s = 0; s < A.spp; s++) {
                 double jx = 0.0, jy = 0.0;
-                if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy);
+                if (A.spp > 1) pcg_in_disc(rng, A.ray_radius, jx, jy, A.cam.indisc_variant);
                 V3<double> O, D;
                 get_ray(A.cam, rng, (double)x, (double)y, jx, jy, O, D);
                 int depth_left = A.max_depth, sp = 0;
@@ -1053,7 +1051,7 @@ __global__ void __launch_bounds__(32) reference_stream_kernel(const RefArgs A, c
                     V3<double> P, N, O2, D2;
                     bool front, alb;
                     hit_record<double>(O, D, bt, mk<double>(g.x, g.y, g.z), S.radius[b], P, N, front);
-                    bool scattered = scatter<double>(S.kind[b], S.params[b], rng, zig, D, P, N, front, O2, D2, alb);
+                    bool scattered = scatter<double>(S.kind[b], S.params[b], rng, zig, D, P, N, front, O2, D2, alb, S.unitvec_variant);
                     if (!scattered) break;
                     if (alb) stk[sp++] = (uint16_t)b;
                     O = O2; D = D2;
@@ -1224,7 +1222,7 @@ __global__ void __launch_bounds__(128) ansi_kernel(const uchar4* __restrict__ im
 }
 
 // Generator parity probe (single thread).
-__global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long long seed, double radius, int n, double* out) {
+__global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long long seed, double radius, int n, double* out, int indisc_variant, int unitvec_variant) {
     __shared__ ZigTables zig;
     zig_load(&zig, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -1234,8 +1232,8 @@ __global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long 
         if (kind == 0) out[i] = __longlong_as_double((long long)pcg_u64(r));
         else if (kind == 1) out[i] = pcg_f64(r);
         else if (kind == 2) out[i] = pcg_norm(r, &zig);
-        else if (kind == 3) { V3<double> v = pcg_unit_vector(r, &zig); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
-        else { double x, y; pcg_in_disc(r, radius, x, y); out[2 * i] = x; out[2 * i + 1] = y; }
+        else if (kind == 3) { V3<double> v = pcg_unit_vector(r, &zig, unitvec_variant); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
+        else { double x, y; pcg_in_disc(r, radius, x, y, indisc_variant); out[2 * i] = x; out[2 * i + 1] = y; }
     }
 }
 
