@@ -157,7 +157,8 @@ typedef struct {
     double trace_kernel_ms; /* device time of the trace kernels alone */
     double trace_launches;  /* how many trace-kernel launches that was (one per pass and device; wavefront: one per bounce stage) */
     double box_tests;       /* TRAY_ACCEL_CLUSTER: conservative box tests evaluated (groups + chunks), summed over rays */
-    double reserved[1];
+    double bounds_violations; /* bounds-check builds (-DTRAY_BOUNDS_CHECK) only: out-of-range table / list / stack / scratch accesses the
+                                 trace kernels refused so far in this process; always 0 in the release build */
 } tray_stats;
 
 /* Creates a context on the given CUDA devices (devices==NULL or n_devices<=0: device 0). */

@@ -53,7 +53,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("sphere_tests", C.c_uint64),
                 ("depth_exhausted", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("launches", C.c_int32), ("n_devices", C.c_int32), ("trace_kernel_ms", C.c_double),
-                ("trace_launches", C.c_double), ("box_tests", C.c_double), ("reserved", C.c_double * 1)]
+                ("trace_launches", C.c_double), ("box_tests", C.c_double), ("bounds_violations", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -205,6 +205,7 @@ struct tray_ctx {
     int bvh_built_on_device = 0;          // what the last upload did (tray_query)
     int cluster_unfilterable = 0;         // spheres of the scene the fp32 filter cannot bound (every ray tests them exactly)
     int indisc_variant = 0, unitvec_variant = 0;  // tray_configure(TRAY_CFG_INDISC / TRAY_CFG_UNITVEC)
+    int debug_fault = 0;                          // bounds-check builds only (negative control)
     bool hdr_is_sums = false;          // last render left raw colour sums (sums_mode != 0)
     uint64_t sums_samples = 0;         // samples per pixel accumulated in them
     int sums_key[6] = {0, 0, 0, 0, 0, 0};  // geometry the sums belong to (w, h, y0, y1, shard_index, shard_count)
@@ -244,6 +245,9 @@ template <> DevScene<double> dev_scene<double>(const tray_ctx* ctx, const Device
     s.n = d.n; s.n_pad = d.n_pad; s.geo = d.geo_d; s.radius = d.radius_d; s.kind = d.kind; s.params = d.params;
     s.fpair = d.fpair; s.filt_mc = d.filt_mc; s.filt_r2max = d.filt_r2max;
     fill_cluster(s, d);
+#ifdef TRAY_BOUNDS_CHECK
+    if (ctx->debug_fault) s.cl_blob_f4 = std::max(0, s.cl_blob_f4 - 256);  // the kernel then stages (and checks against) too small a table
+#endif
     s.unitvec_variant = ctx->unitvec_variant;
     s.bvh = d.bvh_present ? d.bvh : nullptr; s.bvh_leaf_ids = d.bvh_leaf_ids; s.bvh_always = d.bvh_always; s.bvh_n_always = d.bvh_n_always; s.bvh_extent = d.bvh_extent;
     for (int i = 0; i < 3; i++) { s.bg_a[i] = ctx->bg_a[i]; s.bg_b[i] = ctx->bg_b[i]; }
@@ -1199,7 +1203,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
         ctx->split_mode = p->split_mode;
         if (rgba_out && !subset) copy_out(ctx, rgba_out, stride);
         double kernel_ms = 0, trace_ms = 0;
-        unsigned long long seg = 0, exh = 0, bvh_tests = 0, box_tests = 0;
+        unsigned long long seg = 0, exh = 0, bvh_tests = 0, box_tests = 0, violations = 0;
         for (Device& d : ctx->devs) {
             CK(cudaSetDevice(d.dev));
             CK(cudaStreamSynchronize(d.stream));
@@ -1213,9 +1217,9 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             }
             kernel_ms = std::max(kernel_ms, (double)ms);
             trace_ms = std::max(trace_ms, (double)ms2);
-            unsigned long long st[5];
+            unsigned long long st[7];
             CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
-            seg += st[0]; exh += st[1]; bvh_tests += st[3]; box_tests += st[4];
+            seg += st[0]; exh += st[1]; bvh_tests += st[3]; box_tests += st[4]; violations += st[6];
         }
         ctx->have_image = !subset; ctx->have_hdr = true;
         ctx->hdr_is_sums = subset;
@@ -1237,6 +1241,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             // chunk was scanned (pair pre-filter evaluations), box tests counted separately
             stats->sphere_tests = bvh_tests ? bvh_tests : seg * (unsigned long long)ctx->devs[0].n;
             stats->box_tests = (double)box_tests;
+            stats->bounds_violations = (double)violations;
             stats->depth_exhausted = exh;
             stats->kernel_ms = kernel_ms;
             stats->trace_kernel_ms = trace_ms;
@@ -1315,6 +1320,9 @@ int tray_configure(tray_ctx* ctx, int32_t key, int64_t value) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (key == TRAY_CFG_BVH_BUILD && value >= TRAY_BVH_BUILD_AUTO && value <= TRAY_BVH_BUILD_DEVICE) { ctx->bvh_build = (int)value; return TRAY_OK; }
+#ifdef TRAY_BOUNDS_CHECK
+    if (key == 99) { ctx->debug_fault = (int)value; return TRAY_OK; }  // negative control of the bounds-check build: understate the staged table size
+#endif
     if (key == TRAY_CFG_INDISC && value >= 0 && value <= 2) { ctx->indisc_variant = (int)value; return TRAY_OK; }
     if (key == TRAY_CFG_UNITVEC && value >= 0 && value <= 2) { ctx->unitvec_variant = (int)value; return TRAY_OK; }
     return fail(ctx, TRAY_E_INVALID, "tray_configure: unknown key or value");

@@ -22,6 +22,25 @@ constexpr int kCand = TRAY_CH + 8;  // deferred candidates per lane before an in
 constexpr int kBatch = 128;      // samples a warp takes from the global counter at a time
 constexpr unsigned kFull = 0xffffffffu;
 
+// Bounds-check build (-DTRAY_BOUNDS_CHECK, tools/gpu_bounds.sh): every table / list / stack / scratch access of the trace
+// kernels is checked against its allocation and violations are counted in stats[6] (tray_stats.bounds_violations) instead of
+// being executed. compute-sanitizer is not available on the GPU pool this was developed on, so this build -- run over
+// tools/sanitize_run.py, which covers every kernel variant and every table-size remainder -- is the memory-safety evidence;
+// the release build compiles the checks away.
+#ifdef TRAY_BOUNDS_CHECK
+__device__ unsigned long long g_bounds_violations;
+#define TRAY_CHECK(cond) ((cond) ? true : (atomicAdd(&g_bounds_violations, 1ull), false))
+__device__ __forceinline__ unsigned dyn_smem_end() {  // one past the last byte of the CTA's dynamic shared memory
+    unsigned size, base;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(size));
+    extern __shared__ __align__(16) unsigned char smem_probe[];
+    base = (unsigned)__cvta_generic_to_shared(smem_probe);
+    return base + size;
+}
+#else
+#define TRAY_CHECK(cond) true
+#endif
+
 struct TraceArgs {
     DevCamera cam;
     int width, spp, max_depth;
@@ -167,7 +186,7 @@ __device__ __noinline__ void push_candidates(const typename Vec4T<T>::type* __re
     }
     while (mask) {
         int bit = 31 - __clz(mask);
-        cand[ncand * TPB] = (uint16_t)(base + (CH - 1 - bit));
+        if (TRAY_CHECK(ncand < kCand)) cand[ncand * TPB] = (uint16_t)(base + (CH - 1 - bit));
         ncand++;
         mask &= ~(1u << bit);
     }
@@ -288,6 +307,9 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
     // reads valid (unused) memory. One running shared-memory address, immediate offsets.
     static_assert(CH == 8, "the pre-filter loop is written for chunks of 8 spheres");
     auto lds4 = [](float4& v, unsigned addr) {
+#ifdef TRAY_BOUNDS_CHECK
+        if (!TRAY_CHECK(addr + 16u <= dyn_smem_end())) { v = make_float4(0, 0, 0, 0); return; }  // (the last prefetch reads past the table: it must stay inside the allocation)
+#endif
         asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     };
     unsigned mask = 0;
@@ -344,7 +366,7 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
             unsigned m = mask_prev;
             do {  // append in index order: bit CH-1-u <-> sphere (i-CH)+u
                 int bit = 31 - __clz(m);
-                cand[ncand * TPB] = (uint16_t)(i - 1 - bit);
+                if (TRAY_CHECK(ncand < kCand)) cand[ncand * TPB] = (uint16_t)(i - 1 - bit);
                 ncand++;
                 m &= ~(1u << bit);
             } while (m);
@@ -364,6 +386,7 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
 #pragma unroll 1
     for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
         const int id = cand[k * TPB];
+        if (!TRAY_CHECK(k < kCand && id >= 0 && id <= 65535)) continue;  // (the table holds n_pad + 8 entries; ids come from the staged tables)
         typename Vec4T<T>::type g = ggeo[id];
         T h, c, disc, root;
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
@@ -454,9 +477,17 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     const float2 SX = make_float2(ks * fabsf(ix), ks * fabsf(ix)), SY = make_float2(ks * fabsf(iy), ks * fabsf(iy)),
                  SZ = make_float2(ks * fabsf(iz), ks * fabsf(iz));
 
+#ifdef TRAY_BOUNDS_CHECK
+    const unsigned chk_lo = (unsigned)__cvta_generic_to_shared(sblob), chk_hi = chk_lo + (unsigned)S.cl_blob_f4 * 16u;
+    auto lds4 = [&](float4& v, unsigned addr) {  // every table read of the scan stays inside the staged blob
+        if (!TRAY_CHECK(addr >= chk_lo && addr + 16u <= chk_hi && addr + 16u <= dyn_smem_end())) { v = make_float4(0, 0, 0, 0); return; }
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    };
+#else
     auto lds4 = [](float4& v, unsigned addr) {
         asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     };
+#endif
     // Every pair of tests yields its own 2-bit word and the four words of a chunk are merged by a tree, so that the bit
     // gathering is a dependency chain of 4 instructions instead of 8 funnel shifts in a row (the scan is latency-bound).
     auto pair = [&](const float4& g0, const float4& g1) -> unsigned {  // two spheres: 8 packed instructions (see filter_scan)
@@ -529,7 +560,13 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
                     }
                     do {  // bit 7-u <-> slot chunk*8+u
                         const int bit = 31 - __clz(m);
-                        cand[ncand * TPB] = sids[chunk * 8 + 7 - bit];
+#ifdef TRAY_BOUNDS_CHECK
+                        const bool ids_inside = (unsigned)__cvta_generic_to_shared(sids + (chunk * 8 + 7 - bit)) + 2u <= chk_hi;
+#else
+                        const bool ids_inside = true;
+#endif
+                        if (TRAY_CHECK(ids_inside && ncand < kCand && chunk * 8 + 7 - bit < (S.cl_off_box2 >> 3) * 8 && chunk >= 0))
+                            cand[ncand * TPB] = sids[chunk * 8 + 7 - bit];
                         ncand++;
                         m &= ~(1u << bit);
                     } while (m);
@@ -652,7 +689,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 }
                 unsigned avail = gen_avail;
                 unsigned rank = __popc(need & lt_mask);
-                if (!has && rank < avail) {
+                if (!has && rank < avail && TRAY_CHECK(gen_first + rank < 32u)) {
                     my_li = gen_base + gen_first + rank;
                     const double2* q = reinterpret_cast<const double2*>(gpool + gen_first + rank);
 #else
@@ -804,6 +841,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     const int n = xb->count[c][w];
                     if (c < cls || (c == cls && w < warp)) dst += n;
                 }
+            if (!TRAY_CHECK(dst >= 0 && dst < TPB)) dst = tid;
             xb->f[0][dst] = (double)O.x; xb->f[1][dst] = (double)O.y; xb->f[2][dst] = (double)O.z;
             xb->f[3][dst] = (double)D.x; xb->f[4][dst] = (double)D.y; xb->f[5][dst] = (double)D.z;
             xb->f[6][dst] = (double)best_t;
@@ -864,7 +902,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 } else {
                     if (kind != 2) {  // attenuation = albedo; Dielectric's (1,1,1) is an exact identity
                         if constexpr (REGROUP) A.stk_g[(size_t)sp * A.n_slots + slot] = (uint16_t)best;
-                        else stk[sp] = (uint16_t)best;
+                        else if (TRAY_CHECK(sp >= 0 && sp < kMaxDepth && best >= 0 && best < S.n)) stk[sp] = (uint16_t)best;
                         sp++;
                     }
                     O = P; D = D2;
@@ -883,7 +921,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     }
                 }
                 double* out = A.scratch + 3ull * my_li;
-                out[0] = (double)col.x; out[1] = (double)col.y; out[2] = (double)col.z;
+                if (TRAY_CHECK((unsigned long long)my_li < A.n_samples)) { out[0] = (double)col.x; out[1] = (double)col.y; out[2] = (double)col.z; }
                 has = false;
                 O = mk<T>(T(0), T(1e18), T(0)); D = mk<T>(T(0), T(1), T(0));
                 ndone++;
@@ -906,6 +944,9 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         atomicAdd(&A.stats[1], (unsigned long long)nexh);
         if (ntests) atomicAdd(&A.stats[3], ntests);
         if (nbox) atomicAdd(&A.stats[4], nbox);
+#ifdef TRAY_BOUNDS_CHECK
+        if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[6] = g_bounds_violations;  // (running total of the process; read after the kernel)
+#endif
         if (A.progress) atomicAdd(A.progress, (unsigned long long)ndone);
     }
 }
