@@ -369,14 +369,17 @@ def test_full_size_properties(ctx, O):
 
 
 def test_fp32_mode_reports_psnr(ctx):
-    # the fp32 fast path is reported separately with its PSNR against fp64 (no bit-level claim)
+    """The fp32 path is reported separately with its PSNR against fp64 (no bit-level claim; north_star: "fp32 mode reports
+    PSNR"). BASELINE config 2, where bench.py quotes it: measured 52.4 dB, 92.6 % of the pixels within 1 LSB. It is NOT a
+    fast path any more: with the two-level closest hit the strict fp64 default is as fast."""
     scene = ray.RichScene(rand.New(2))
-    a = tracer(320, 180, 16, 50).Render(scene).astype(np.float64)
-    b = tracer(320, 180, 16, 50, precision=ray.FP32).Render(scene).astype(np.float64)
+    a = tracer(1920, 1080, 64, 50).Render(scene).astype(np.float64)
+    b = tracer(1920, 1080, 64, 50, precision=ray.FP32).Render(scene).astype(np.float64)
     mse = ((a[:, :, :3] - b[:, :, :3]) ** 2).mean()
     psnr = 10 * np.log10(255.0 ** 2 / mse)
-    print("fp32 PSNR vs fp64: %.2f dB" % psnr)
-    assert psnr > 20.0
+    within = (np.abs(a[:, :, :3] - b[:, :, :3]).max(axis=2) <= 1).mean()
+    print("fp32 PSNR vs fp64: %.2f dB, %.4f of the pixels within 1 LSB" % (psnr, within))
+    assert psnr > 50.0 and within > 0.9
 
 
 # ---- "next" row 8(f)-1: on-device BiLinear downscale + half-block ANSI frame (BASELINE config 5) ---------------

@@ -450,7 +450,7 @@ int launch_trace(const tray_ctx* ctx, Device& d, const TraceArgs& A, int precisi
     else if (precision == TRAY_FP64_STRICT) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), true, use, regroup);
     else if (precision == TRAY_FP64_STRICT_BRUTE) TraceLaunch<double, false>::run(d, A, dev_scene<double>(ctx, d), ctx->host_geo_d.data(), false, use64);
     // fp32 fast path: the same conservative pre-filter (it proves a miss in exact arithmetic), survivors tested in fp32
-    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, use == kUseBvh ? kUseLinear : use, regroup || auto_layout);  // fp32: regroup measures faster
+    else TraceLaunch<float, true>::run(d, A, dev_scene<float>(ctx, d), ctx->host_geo_f.data(), true, use == kUseBvh ? kUseLinear : use, regroup);
     return 1;
 }
 
@@ -1217,9 +1217,14 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
             }
             kernel_ms = std::max(kernel_ms, (double)ms);
             trace_ms = std::max(trace_ms, (double)ms2);
-            unsigned long long st[7];
+            unsigned long long st[5];
             CK(cudaMemcpy(st, d.stats, sizeof st, cudaMemcpyDeviceToHost));
-            seg += st[0]; exh += st[1]; bvh_tests += st[3]; box_tests += st[4]; violations += st[6];
+            seg += st[0]; exh += st[1]; bvh_tests += st[3]; box_tests += st[4];
+#ifdef TRAY_BOUNDS_CHECK
+            unsigned long long gv = 0;  // running total of this device in this process
+            CK(cudaMemcpyFromSymbol(&gv, g_bounds_violations, sizeof gv));
+            violations += gv;
+#endif
         }
         ctx->have_image = !subset; ctx->have_hdr = true;
         ctx->hdr_is_sums = subset;

@@ -944,9 +944,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         atomicAdd(&A.stats[1], (unsigned long long)nexh);
         if (ntests) atomicAdd(&A.stats[3], ntests);
         if (nbox) atomicAdd(&A.stats[4], nbox);
-#ifdef TRAY_BOUNDS_CHECK
-        if (blockIdx.x == 0 && threadIdx.x == 0) A.stats[6] = g_bounds_violations;  // (running total of the process; read after the kernel)
-#endif
+
         if (A.progress) atomicAdd(A.progress, (unsigned long long)ndone);
     }
 }
