@@ -86,7 +86,10 @@ for l in regions.splitlines():
     m = l.split()
     if len(m) >= 6 and m[-1].endswith("%") and m[-2].endswith("%"):
         fn = " ".join(m[1:-4])
-        smp = float(m[-2].rstrip("%")) / 100
+        try:
+            smp = float(m[-2].rstrip("%")) / 100
+        except ValueError:
+            continue
         for g, names in GROUPS.items():
             if fn in names or m[0] in names:
                 share[g] += smp

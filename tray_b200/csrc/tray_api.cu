@@ -272,6 +272,7 @@ DevCamera dev_camera(const tray_camera* c, int indisc_variant = 0) {
         d.du[i] = c->defocus_u[i]; d.dv[i] = c->defocus_v[i];
     }
     d.aperture = c->aperture; d.focus_distance = c->focus_distance; d.focal_length = c->focal_length;
+    d.focus_time = c->focus_distance / c->focal_length;  // (host build: -ffp-contract=off, IEEE double division like the device's)
     return d;
 }
 

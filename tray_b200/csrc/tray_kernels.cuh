@@ -525,66 +525,82 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     const unsigned a_box2 = sbase + (unsigned)S.cl_off_box2 * 16u, a_box1 = sbase + (unsigned)S.cl_off_box1 * 16u;
     const uint16_t* sids = reinterpret_cast<const uint16_t*>(sblob + S.cl_off_ids);
     const int n_always = S.cl_always_groups, n_words = S.cl_real_groups >> 3;
-    // words -n_always..-1: one always-group each (no box tests); words 0..: 8 real groups behind their boxes.
-    // One code site tests 8 boxes (a word of groups or the chunks of a group), one site scans a chunk: the walk is written
-    // as a loop that decides what comes next, so that the hot code is 104 + 70 instructions instead of two copies of each.
+    // words -n_always..-1: one always-group each (no box tests); words 0..: 8 real groups = 64 chunks behind their boxes.
+    // Per word: (1) the 8 group boxes, warp union; (2) the chunk boxes of every marked group, each lane collecting its own
+    // 64-bit chunk mask -- no cross-lane step between groups, so their tests overlap --, then ONE union of the mask; (3) the
+    // marked chunks through the pair pre-filter, software-pipelined by half chunks (the loads of the next half / next chunk
+    // are in flight while a half is evaluated). The scan is latency-bound: the point of this shape is few serial points.
 #pragma unroll 1
     for (int w = -n_always; w < n_words; w++) {
-        unsigned ug = 0, uc = 0;   // warp-uniform: groups of this word / chunks of group g still to visit
-        int g = 0;
-        bool word_done = false;    // the word's own boxes have been tested
-        if (w < 0) { g = S.cl_real_groups + (w + n_always); uc = w == -1 ? S.cl_always_last : 0xffu; word_done = true; }
+        unsigned long long ucm;  // warp-uniform: chunks of this word to scan, bit 63-p <-> chunk cbase+p
+        int cbase;
+        if (w < 0) {
+            cbase = (S.cl_real_groups + (w + n_always)) * 8;
+            ucm = (unsigned long long)(w == -1 ? S.cl_always_last : 0xffu) << 56;
+        } else {
+            cbase = w * 64;
+            const unsigned ad1 = a_box1 + (unsigned)w * (4u * 48u);
+            unsigned ug = may_hit8(merge4(boxes(ad1), boxes(ad1 + 48), boxes(ad1 + 96), boxes(ad1 + 144)));
+            nboxes += 8;
+            unsigned long long cm = 0;
 #pragma unroll 1
-        for (;;) {
-            if (uc) {
-                const int cbit = 31 - __clz(uc);
-                uc &= ~(1u << cbit);
-                const int chunk = g * 8 + 7 - cbit;
-                const unsigned ad = sbase + (unsigned)chunk * 128u;
-                float4 a0, a1, a2, a3, b0, b1, b2, b3;
-                lds4(a0, ad); lds4(a1, ad + 16); lds4(a2, ad + 32); lds4(a3, ad + 48);
-                lds4(b0, ad + 64); lds4(b1, ad + 80); lds4(b2, ad + 96); lds4(b3, ad + 112);
-                const unsigned mask = merge4(pair(a0, a1), pair(a2, a3), pair(b0, b1), pair(b2, b3));
-                nchunks++;
-                unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
-                if (m) {
-                    if (ncand > kCand - 8) {  // list about to overflow (rare): run the exact test on what is queued
-                        T fx_ = ox, fy_ = oy, fz_ = oz, gx_ = dx, gy_ = dy, gz_ = dz;
-                        if (parked) {  // TRAY_PARK_STATE: the fp64 ray waits in shared memory during the scan
-                            fx_ = T(parked[0]); fy_ = T(parked[TPB]); fz_ = T(parked[2 * TPB]);
-                            gx_ = T(parked[3 * TPB]); gy_ = T(parked[4 * TPB]); gz_ = T(parked[5 * TPB]);
-                        }
-                        const BestHit<T> bh = flush_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, fx_, fy_, fz_, gx_, gy_, gz_, best_t, best);
-                        best_t = bh.t; best = bh.id;
-                        ncand = 0;
-                    }
-                    do {  // bit 7-u <-> slot chunk*8+u
-                        const int bit = 31 - __clz(m);
-#ifdef TRAY_BOUNDS_CHECK
-                        const bool ids_inside = (unsigned)__cvta_generic_to_shared(sids + (chunk * 8 + 7 - bit)) + 2u <= chk_hi;
-#else
-                        const bool ids_inside = true;
-#endif
-                        if (TRAY_CHECK(ids_inside && ncand < kCand && chunk * 8 + 7 - bit < (S.cl_off_box2 >> 3) * 8 && chunk >= 0))
-                            cand[ncand * TPB] = sids[chunk * 8 + 7 - bit];
-                        ncand++;
-                        m &= ~(1u << bit);
-                    } while (m);
-                }
-                continue;
-            }
-            unsigned ad;
-            if (!word_done) ad = a_box1 + (unsigned)w * (4u * 48u);
-            else {
-                if (!ug) break;
+            while (ug) {
                 const int gbit = 31 - __clz(ug);
                 ug &= ~(1u << gbit);
-                g = w * 8 + 7 - gbit;
-                ad = a_box2 + (unsigned)g * (4u * 48u);
+                const int gi = 7 - gbit;
+                const unsigned ad2 = a_box2 + (unsigned)(w * 8 + gi) * (4u * 48u);
+                const unsigned m8 = merge4(boxes(ad2), boxes(ad2 + 48), boxes(ad2 + 96), boxes(ad2 + 144));
+                cm |= (unsigned long long)(off ? 0xffu : (~m8 & 0xffu)) << (56 - 8 * gi);
+                nboxes += 8;
             }
-            const unsigned u8 = may_hit8(merge4(boxes(ad), boxes(ad + 48), boxes(ad + 96), boxes(ad + 144)));
-            nboxes += 8;
-            if (!word_done) { ug = u8; word_done = true; } else uc = u8;
+            if (!has) cm = 0;
+            const unsigned lo = __reduce_or_sync(kFull, (unsigned)cm), hi = __reduce_or_sync(kFull, (unsigned)(cm >> 32));
+            ucm = ((unsigned long long)hi << 32) | lo;
+        }
+        if (ucm == 0) continue;
+        int pos = __clzll((long long)ucm);
+        unsigned ad = sbase + (unsigned)(cbase + pos) * 128u;
+        float4 a0, a1, a2, a3, b0, b1, b2, b3;
+        lds4(a0, ad); lds4(a1, ad + 16); lds4(a2, ad + 32); lds4(a3, ad + 48);
+#pragma unroll 1
+        for (;;) {
+            lds4(b0, ad + 64); lds4(b1, ad + 80); lds4(b2, ad + 96); lds4(b3, ad + 112);
+            const unsigned long long rest = ucm & ~(0x8000000000000000ull >> pos);
+            const unsigned p0 = pair(a0, a1), p1 = pair(a2, a3);
+            const int npos = rest ? __clzll((long long)rest) : pos;   // (last chunk: the prefetch re-reads it, harmlessly)
+            const unsigned nad = sbase + (unsigned)(cbase + npos) * 128u;
+            lds4(a0, nad); lds4(a1, nad + 16); lds4(a2, nad + 32); lds4(a3, nad + 48);
+            const unsigned mask = merge4(p0, p1, pair(b0, b1), pair(b2, b3));
+            nchunks++;
+            unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
+            if (m) {
+                const int chunk = cbase + pos;
+                if (ncand > kCand - 8) {  // list about to overflow (rare): run the exact test on what is queued
+                    T fx_ = ox, fy_ = oy, fz_ = oz, gx_ = dx, gy_ = dy, gz_ = dz;
+                    if (parked) {  // TRAY_PARK_STATE: the fp64 ray waits in shared memory during the scan
+                        fx_ = T(parked[0]); fy_ = T(parked[TPB]); fz_ = T(parked[2 * TPB]);
+                        gx_ = T(parked[3 * TPB]); gy_ = T(parked[4 * TPB]); gz_ = T(parked[5 * TPB]);
+                    }
+                    const BestHit<T> bh = flush_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, fx_, fy_, fz_, gx_, gy_, gz_, best_t, best);
+                    best_t = bh.t; best = bh.id;
+                    ncand = 0;
+                }
+                do {  // bit 7-u <-> slot chunk*8+u
+                    const int bit = 31 - __clz(m);
+#ifdef TRAY_BOUNDS_CHECK
+                    const bool ids_inside = (unsigned)__cvta_generic_to_shared(sids + (chunk * 8 + 7 - bit)) + 2u <= chk_hi;
+#else
+                    const bool ids_inside = true;
+                    (void)ids_inside;
+#endif
+                    if (TRAY_CHECK(ids_inside && ncand < kCand && chunk * 8 + 7 - bit < (S.cl_off_box2 >> 3) * 8 && chunk >= 0))
+                        cand[ncand * TPB] = sids[chunk * 8 + 7 - bit];
+                    ncand++;
+                    m &= ~(1u << bit);
+                } while (m);
+            }
+            if (!rest) break;
+            ucm = rest; pos = npos; ad = nad;
         }
     }
 }
