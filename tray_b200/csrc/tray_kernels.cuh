@@ -383,66 +383,25 @@ template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                        T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
     const T tmin = front_epsilon<T>();
-    const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
-    const T lo = tmin * a * dn;
-    if constexpr (sizeof(T) == 8) {
-        // fp64: two candidates per step. The accepted root of a sphere does not depend on the other candidates (only the
-        // comparison with the best so far does, and that is applied in list order at the end of the step), so the two
-        // exact tests -- sphere terms, square root, near / far quotient -- run as two interleaved dependency chains.
 #pragma unroll 1
-        for (int k = 0; k < ncand; k += 2) {
-            const bool two = k + 1 < ncand;
-            const int id0 = cand[k * TPB], id1 = two ? cand[(k + 1) * TPB] : id0;
-            if (!TRAY_CHECK(k + 1 < kCand + 1 && id0 >= 0 && id0 <= 65535 && id1 >= 0 && id1 <= 65535)) continue;
-            const typename Vec4T<T>::type g0 = ggeo[id0], g1 = ggeo[id1];
-            T h0, c0, disc0, h1, c1, disc1;
-            sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g0.x, g0.y, g0.z, g0.w, h0, c0, disc0);
-            sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g1.x, g1.y, g1.z, g1.w, h1, c1, disc1);
-            const bool live0 = !certainly_missed(h0, c0, disc0), live1 = two && !certainly_missed(h1, c1, disc1);
-            if (!live0 && !live1) continue;
-            const D2 sq = sqrt2_f64((double)disc0, (double)disc1);
-            const T hi = best_t * a * up;
-            // near roots (h - sqrt)/a: only quotients that can land in (tmin, best_t] are taken
-            const T n0 = h0 - T(sq.a), n1 = h1 - T(sq.b);
-            const bool qn0 = live0 && n0 > lo && n0 < hi, qn1 = live1 && n1 > lo && n1 < hi;
-            T r0 = T(0), r1 = T(0);
-            bool ok0 = false, ok1 = false;                 // this sphere has an accepted root r
-            bool far0 = live0 && !(n0 > lo), far1 = live1 && !(n1 > lo);   // near root certainly <= tmin: the far root decides
-            if (qn0 || qn1) {
-                const D2 q = div2_f64((double)n0, (double)n1, (double)a);
-                if (qn0) { if (T(q.a) > tmin) { r0 = T(q.a); ok0 = true; } else far0 = true; }
-                if (qn1) { if (T(q.b) > tmin) { r1 = T(q.b); ok1 = true; } else far1 = true; }
-            }
-            const T f0 = h0 + T(sq.a), f1 = h1 + T(sq.b);
-            const bool qf0 = far0 && f0 > lo && f0 < hi, qf1 = far1 && f1 > lo && f1 < hi;
-            if (qf0 || qf1) {
-                const D2 q = div2_f64((double)f0, (double)f1, (double)a);
-                if (qf0 && T(q.a) > tmin) { r0 = T(q.a); ok0 = true; }
-                if (qf1 && T(q.b) > tmin) { r1 = T(q.b); ok1 = true; }
-            }
-            if (ok0 && (r0 < best_t || (r0 == best_t && id0 < best))) { best_t = r0; best = id0; }
-            if (ok1 && (r1 < best_t || (r1 == best_t && id1 < best))) { best_t = r1; best = id1; }
-        }
-    } else {
-#pragma unroll 1
-        for (int k = 0; k < ncand; k++) {
-            const int id = cand[k * TPB];
-            if (!TRAY_CHECK(k < kCand && id >= 0 && id <= 65535)) continue;
-            typename Vec4T<T>::type g = ggeo[id];
-            T h, c, disc, root;
-            sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
-            if (certainly_missed(h, c, disc)) continue;
-            T sq = tsqrt(disc);
-            const T hi = best_t * a * up;
-            T x = h - sq;
-            bool ok = false;
+    for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
+        const int id = cand[k * TPB];
+        if (!TRAY_CHECK(k < kCand && id >= 0 && id <= 65535)) continue;  // (the table holds n_pad + 8 entries; ids come from the staged tables)
+        typename Vec4T<T>::type g = ggeo[id];
+        T h, c, disc, root;
+        sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
+        if (certainly_missed(h, c, disc)) continue;
+        T sq = tsqrt(disc);
+        const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
+        const T hi = best_t * a * up, lo = tmin * a * dn;
+        T x = h - sq;
+        bool ok = false;
+        if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+        if (!ok) {
+            x = h + sq;
             if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
-            if (!ok) {
-                x = h + sq;
-                if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
-            }
-            if (ok) { best_t = root; best = id; }
         }
+        if (ok) { best_t = root; best = id; }
     }
 }
 
