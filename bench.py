@@ -7,7 +7,7 @@
 
 A "step" is one full render of the workload (one pass of the hot path over every pixel x sample).
 N=1 workload: BASELINE.json configs[1] (RichScene seed 2, 1920x1080, 64 rays/pixel, depth 50, fp64).
-N>1 workload: configs[2] (3840x2160, 256 rays/pixel, depth 50), interleaved 8-row bands across ranks,
+N>1 workload: configs[2] (3840x2160, 256 rays/pixel, depth 50), interleaved rows across ranks,
 no data-path collective (each rank writes its own rows of the shared host image).
 
 Timed regions:
@@ -525,7 +525,7 @@ def run_ours(args):
             if rank == 0:
                 dd = np.abs(img_s[:, :, :3].astype(np.int16) - main_img[:, :, :3].astype(np.int16)).max(axis=2)
                 rec["vs_tiles_image"] = {"pixels_identical_frac": float((dd == 0).mean()), "pixels_within_1lsb_frac": float((dd <= 1).mean())}
-                rec["within_2pct_of_tiles"] = bool(abs(rec["value"] / value - 1) <= 0.02)
+                rec["not_more_than_2pct_slower_than_tiles"] = bool(rec["value"] / value >= 0.98)
             alts.append(rec)
         host_barrier()
         if rank == 0:
@@ -556,8 +556,8 @@ def run_ours(args):
                     v = g_paths / (g_ms * 1e-3) / 1e6
                     inctx[name] = {"value": v, "unit": "Mpaths/s", "ms_per_step": g_ms / k, "e2e_value": stg["paths"] / (g_wall * 1e-3) / 1e6,
                                    "n_devices": int(stg["n_devices"]), "pixels_identical_frac": float((dd == 0).mean()),
-                                   "pixels_within_1lsb_frac": float((dd <= 1).mean()), "within_2pct_of_multiprocess_tiles": bool(abs(v / value - 1) <= 0.02)}
-                inctx["note"] = ("one process drives all %d GPUs through one tray_ctx (tray_init(devices, n)): 'tiles' = interleaved 8-row bands, device-to-host "
+                                   "pixels_within_1lsb_frac": float((dd <= 1).mean()), "not_more_than_2pct_slower_than_multiprocess_tiles": bool(v / value >= 0.98)}
+                inctx["note"] = ("one process drives all %d GPUs through one tray_ctx (tray_init(devices, n)): 'tiles' = interleaved rows, device-to-host "
                                  "gather only, must equal the multi-process image bit for bit; 'samples' = device g traces samples s == g (mod G), combine_kernel on "
                                  "device 0 sums the partial sums through peer pointers over NVLink and applies 1/N + sRGB (<= 1 LSB); device time = max over devices") % world
                 multi_gpu["in_context"] = inctx

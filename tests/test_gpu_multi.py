@@ -1,4 +1,4 @@
-"""Multi-device context (one process, G devices): tile mode (interleaved 8-row bands, device-to-host gather only) and
+"""Multi-device context (one process, G devices): tile mode (interleaved rows, device-to-host gather only) and
 sample-split mode (partial sums reduced over NVLink peer pointers inside the combine kernel). Needs >= 2 GPUs."""
 import numpy as np
 import pytest

@@ -1,5 +1,5 @@
 """N>1 path on CPU: world_size-2 gloo run of the tile-sharding host logic bench.py uses. Each rank renders only
-its own 8-row bands (here with the oracle standing in for the device) into a shared host image with no
+its own interleaved rows (here with the oracle standing in for the device) into a shared host image with no
 data-path collective; the union must be bit-identical to the unsharded image, and a MAX all_reduce carries
 the timing the way bench.py reports it."""
 import os

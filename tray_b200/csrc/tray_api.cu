@@ -734,7 +734,7 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
 }
 
 constexpr int kClusterMaxSpheres = 4096;  // 64 groups x 8 chunks x 8 spheres: 8 words of group boxes per segment at most
-constexpr int kBandRows = 8;
+constexpr int kBandRows = 1;  // rows per band of the tile split: single rows balance best (2160 rows over 8 shards: 270 each; 8-row bands gave 33 or 34 bands and 0.94 scaling efficiency at 8 GPUs)
 // Scratch per pass, in samples (x24 bytes), whole pixels per pass: at least this much, more when the device has the room
 // (tray_render sizes a pass from cudaMemGetInfo so that a device's whole share is one pass when it fits).
 constexpr unsigned long long kPassSamples = 144ull << 20;

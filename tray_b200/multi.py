@@ -1,6 +1,6 @@
 """One process per GPU (torchrun): the two ways the path partitions across B200s.
 
-  render_tiles         interleaved 8-row bands, rank r renders bands b == r (mod world); no data-path collective,
+  render_tiles         interleaved rows, rank r renders rows y == r (mod world); no data-path collective,
                        every rank writes its own rows of the caller's (shared) host image.
   render_sample_split  rank r renders samples s == r (mod world) of every pixel into fp64 colour sums that stay on the
                        device; ONE exchange step: a sum-reduce of that buffer to rank 0 over NCCL (NVLink / NVSwitch);

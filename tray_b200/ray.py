@@ -516,11 +516,11 @@ def New(width, height):
     return Tracer(width, height)
 
 
-BAND_ROWS = 8  # kBandRows in csrc/tray_api.cu
+BAND_ROWS = 1  # kBandRows in csrc/tray_api.cu
 
 
 def shard_rows(y0, y1, shard_index, shard_count, band_rows=BAND_ROWS):
-    """Rows of [y0,y1) that shard `shard_index` of `shard_count` renders in tile mode: 8-row bands, round-robin
+    """Rows of [y0,y1) that shard `shard_index` of `shard_count` renders in tile mode: rows, round-robin
     (same rule as tray_render; the reference's analogue is the row-chunk work queue, ray/tracer.go:93-103)."""
     if shard_count <= 1:
         return list(range(y0, y1))
