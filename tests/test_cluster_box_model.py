@@ -128,7 +128,9 @@ def test_rich_scene_layout():
 
 # ---- exact model of the slab test ---------------------------------------------------------------------------------
 
-def box_ray_constants(o, d, cl_r):
+def box_ray_constants(o, d, cl_r, rcp_ulps=(0, 0, 0)):
+    """rcp_ulps: the device takes 1/d_k with MUFU.RCP (within 1 ulp of the quotient); the model pushes the correctly rounded
+    quotient by -1, 0 or +1 ulp per axis so that the attack covers the whole error interval."""
     a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
     ln = math.sqrt(a)                                   # Unit(D) of the RayColor step (ray/vec3.go:117-120), fp64
     fd = [F32(d[k] / ln) for k in range(3)]
@@ -138,11 +140,14 @@ def box_ray_constants(o, d, cl_r):
         v = fd[k]
         if abs(v) < lim:
             v = F32(math.copysign(float(lim), float(v)))
-        inv.append(F32(1.0) / v)
+        q = F32(1.0) / v
+        if rcp_ulps[k]:
+            q = np.nextafter(q, F32(np.inf) if rcp_ulps[k] > 0 else F32(-np.inf))
+        inv.append(F32(q))
     nq = [-F32(o[k] * float(inv[k])) for k in range(3)]
     mo = F32(1.0000002) * max(abs(F32(o[0])), abs(F32(o[1])), abs(F32(o[2])))
     R = F32(cl_r) + mo
-    ks = F32(12.0) * U32 * R
+    ks = F32(16.0) * U32 * R
     sl = [ks * abs(inv[k]) for k in range(3)]
     off = not (mo < F32(1e6)) or not (0.0 < a < 1.7976931348623157e308)
     return inv, nq, sl, off
@@ -206,7 +211,7 @@ def test_box_test_never_culls_a_sphere_the_strict_test_would_hit():
         o = tuple(float(v) for v in o)
         hit = pyref.sphere_hit(c, r, o, d, 1e-6, math.inf)
         hits += hit is not None
-        missed = box_says_missed(box_ray_constants(o, d, cl_r), bc, be)
+        missed = box_says_missed(box_ray_constants(o, d, cl_r, tuple(int(v) for v in rs.randint(-1, 2, 3))), bc, be)
         if missed:
             culled += 1
             assert hit is None, (trial, kind, o, d, c, r)

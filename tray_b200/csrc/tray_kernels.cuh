@@ -428,17 +428,18 @@ __device__ __noinline__ BestHit<T> flush_candidates_lex(const typename Vec4T<T>:
 // Spheres the filter cannot bound (|C| or r^2 > 256, non-finite) and very large ones sit in "always" groups that every
 // ray scans. On the benchmark scene a warp scans about 5 of 62 chunks per segment (tools/cluster_sim.py).
 //
-// The slab test of a box (centre c, half extent e, fp32) for the ray O + d t, d = D/|D|, per axis k:
-//   inv = fl32(1/d_k) (|d_k| clamped to >= 2^-60), nq = -fl32(O_k*inv), ai = |inv|, sl = 12 u R ai   (per ray; u = 2^-24,
-//                                                                     R = max|box coordinate| + |O|inf)
+// The slab test of a box (centre c, half extent e, fp32) for the ray O + d t, d = Unit(D), per axis k:
+//   inv = rcp(fl32(d_k)) (MUFU.RCP, |d_k| clamped to >= 2^-60), nq = -fl32(O_k*inv), ai = |inv|, sl = 16 u R ai   (per ray;
+//                                                                     u = 2^-24, R = max|box coordinate| + |O|inf)
 //   A = fma(c, inv, nq)   B = fma(e, ai, sl)   near = A - B   far = A + B
 //   miss  <=>  min_k far < max_k near  or  min_k far < 0          (sign bits of two words, one LOP3)
-// If the exact ray meets the box at some t* >= 0 then for every axis |(c-O)inv - t*| <= e ai + 1.01 u R ai (inv is the
-// exact reciprocal of a direction within 2u of d_k), A is off by <= 2.01 u R ai (rounding of O*inv and of the fma), B may
-// fall short by u R ai, near/far round by <= 2 u R ai: 6.1 u R ai in all. A hit the strict fp64 Sphere.Hit reports lies
-// within sqrt(160 eps) R = 1.33e-7 R = 2.2 u R of the sphere along the true ray (its discriminant is exact to 20 eps a
-// (|C-O|^2 + r^2)), and the boxes are padded on top of that: 8.3 < 12, so near_k <= t* <= far_k for every k and the test
-// cannot report a miss. tests/test_cluster_box_model.py replays the test in exact single-rounded arithmetic.
+// If the exact ray meets the box at some t* >= 0 then for every axis |(c-O)inv - t*| <= e ai + 3.03 u R ai (inv is the exact
+// reciprocal of a direction within 3u of d_k: one rounding of d_k to fp32, 2u of the approximate reciprocal), A is off by
+// <= 2.01 u R ai (rounding of O*inv and of the fma), B may fall short by u R ai, near/far round by <= 2 u R ai: 8.1 u R ai
+// in all. A hit the strict fp64 Sphere.Hit reports lies within sqrt(160 eps) R = 1.33e-7 R = 2.2 u R of the sphere along the
+// true ray (its discriminant is exact to 20 eps a (|C-O|^2 + r^2)), and the boxes are padded on top of that: 10.3 < 16, so
+// near_k <= t* <= far_k for every k and the test cannot report a miss. tests/test_cluster_box_model.py replays the test in
+// exact single-rounded arithmetic with the reciprocal pushed to either end of its error interval.
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4* sblob, const typename Vec4T<T>::type* __restrict__ ggeo,
                                              uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a, T udx, T udy, T udz,
@@ -464,13 +465,15 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
     const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
     // ---- per-ray constants of the box test ----
-    auto rcp = [](float d) {
+    auto rcp = [](float d) {  // MUFU.RCP: within 1 ulp (2u) of 1/d; the operand is a normal number and so is the result
         const float lim = 8.6736174e-19f;  // 2^-60
-        return rcp_f32(fabsf(d) < lim ? copysignf(lim, d) : d);
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(d) < lim ? copysignf(lim, d) : d));
+        return r;
     };
     const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
     const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
-    const float ks = 12.0f * u32 * R;
+    const float ks = 16.0f * u32 * R;
     const float2 IX = make_float2(ix, ix), IY = make_float2(iy, iy), IZ = make_float2(iz, iz);
     const float2 NQX = make_float2(nqx, nqx), NQY = make_float2(nqy, nqy), NQZ = make_float2(nqz, nqz);
     const float2 AX = make_float2(fabsf(ix), fabsf(ix)), AY = make_float2(fabsf(iy), fabsf(iy)), AZ = make_float2(fabsf(iz), fabsf(iz));
