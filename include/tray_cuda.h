@@ -247,6 +247,12 @@ TRAY_API int tray_first_hit(tray_ctx *ctx, const tray_camera *cam, int32_t width
  * 1 Float64, 2 NormFloat64, 3 UnitVector (3 per draw), 4 InDisc(radius) (2 per draw). */
 TRAY_API int tray_rng_dump(tray_ctx *ctx, int32_t kind, uint64_t idx, uint64_t seed, double radius, int32_t n, double *out);
 
+/* Parity probe for the device's IEEE division / square root routines (one shared reciprocal per divisor):
+ * kind 0: (a[i], a[i+1], a[i+2]) / b[i] (3 results per element, indices mod n), 1: a[i] / b[i] through the shared-reciprocal
+ * form, 2: sqrt(a[i]), 3: a[i] / b[i] as the compiler emits it. The Go reference gets these from the CPU's IEEE instructions
+ * (ray/vec3.go:60-75 Unit / SDiv, ray/objects.go:90-100). */
+TRAY_API int tray_arith_probe(tray_ctx *ctx, int32_t kind, const double *a, const double *b, int32_t n, double *out);
+
 /* Parity probe for the on-device sRGB store (ColorF.ToSRGBA, ray/vec3.go:173-180). */
 TRAY_API int tray_linear_to_srgb(tray_ctx *ctx, const double *x, int32_t n, uint8_t *out);
 

@@ -58,6 +58,38 @@ def test_device_rng_known_answer_and_golden(ctx):
     assert np.array_equal(ctx.rng_dump(4, 7, 42, 64, 0.5), g["rng_disc"])
 
 
+def test_device_division_and_sqrt_are_ieee(ctx):
+    """The device's out-of-line fp64 division (one refined reciprocal shared by the quotients of a divisor) and square root
+    return the correctly rounded IEEE results -- what Go gets from DIVSD / SQRTSD (ray/vec3.go:60-75, ray/objects.go:90-100) --
+    on random operands over the whole exponent range and on the edge cases of the fast-path test (zeros, tiny, huge,
+    subnormal, infinite, NaN operands, divisors with an all-ones mantissa)."""
+    rng = np.random.default_rng(12345)
+    n = 1 << 20
+    mant = lambda k: rng.uniform(1.0, 2.0, k) * rng.choice([-1.0, 1.0], k)
+    a = np.concatenate([mant(n) * 2.0 ** rng.integers(-40, 40, n), mant(n) * 2.0 ** rng.integers(-1074, 1024, n), rng.normal(size=n)])
+    b = np.concatenate([mant(n) * 2.0 ** rng.integers(-40, 40, n), mant(n) * 2.0 ** rng.integers(-1074, 1024, n), rng.uniform(0.1, 3.0, n)])
+    ones = np.nextafter(2.0 ** rng.integers(-30, 30, 4096).astype(np.float64) * 2, 0)  # 1.111...1 x 2^k
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, np.inf, -np.inf, np.nan,
+                     1e-200, 1e200, 2.0 ** -120, np.nextafter(2.0 ** -120, 0), 2.0 ** 1017, 2.0 ** -1017, 3.0, 1 / 3.0, 1e-37, 1e-39])
+    ea, eb = np.meshgrid(edge, edge)
+    a = np.concatenate([a, ea.ravel(), rng.normal(size=4096), ones])
+    b = np.concatenate([b, eb.ravel(), ones, rng.normal(size=4096)])
+    with np.errstate(all="ignore"):
+        want = a / b
+        q3 = ctx.arith_probe(0, a, b)
+        for k in range(3):
+            assert np.array_equal(q3[:, k].view(np.uint64) | (np.isnan(q3[:, k]) * np.uint64(0xfff8000000000000)),
+                                  (np.roll(a, -k) / b).view(np.uint64) | (np.isnan(np.roll(a, -k) / b) * np.uint64(0xfff8000000000000)))
+        for kind in (1, 3):
+            got = ctx.arith_probe(kind, a, b)
+            same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (kind, a[~same][:5], b[~same][:5])
+        x = np.abs(a)
+        got = ctx.arith_probe(2, x, x)
+        assert np.array_equal(got.view(np.uint64), np.sqrt(x).view(np.uint64)) or (np.isnan(got) == np.isnan(np.sqrt(x))).all() and \
+            np.array_equal(got[~np.isnan(got)], np.sqrt(x)[~np.isnan(got)])
+
+
 def test_device_srgb_store(ctx, O):
     x = np.concatenate([[0.0, 1.0, 0.5, -0.5, 1.5, 0.25, 0.75, np.nan, 0.0031308, np.nextafter(0.0031308, 1)],
                         np.linspace(-0.01, 1.01, 50001), np.random.default_rng(1).random(100000) ** 3])

@@ -21,7 +21,7 @@ CFG_INDISC, CFG_UNITVEC = 2, 3
 EXPORTS = ("tray_init", "tray_destroy", "tray_last_error", "tray_abi_version", "tray_scene_upload", "tray_render",
            "tray_read_image", "tray_read_hdr", "tray_first_hit", "tray_rng_dump", "tray_linear_to_srgb",
            "tray_progress", "tray_measure_peak", "tray_present", "tray_device_sums", "tray_resolve_sums", "tray_png_bound", "tray_encode_png", "tray_configure", "tray_query", "tray_upload_frame",
-           "tray_cluster_tables")
+           "tray_cluster_tables", "tray_arith_probe")
 
 
 class TrayError(RuntimeError):
@@ -107,6 +107,7 @@ def lib():
         L.tray_first_hit.argtypes = [C.c_void_p, C.POINTER(CameraC), C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.tray_rng_dump.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_double, C.c_int32, C.c_void_p]
         L.tray_linear_to_srgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.tray_arith_probe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.tray_present.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                    C.POINTER(C.c_double)]
         L.tray_device_sums.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]

@@ -1423,6 +1423,25 @@ int tray_rng_dump(tray_ctx* ctx, int32_t kind, uint64_t idx, uint64_t seed, doub
     return TRAY_OK;
 }
 
+int tray_arith_probe(tray_ctx* ctx, int32_t kind, const double* a, const double* b, int32_t n, double* out) {
+    if (!ctx) return TRAY_E_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!a || !b || !out || n <= 0 || kind < 0 || kind > 3) return fail(ctx, TRAY_E_INVALID, "tray_arith_probe: bad argument");
+    try {
+        Device& d = ctx->devs[0];
+        CK(cudaSetDevice(d.dev));
+        const int per = kind == 0 ? 3 : 1;
+        DevTmp t_a(sizeof(double) * n), t_b(sizeof(double) * n), t_o(sizeof(double) * n * per);
+        CK(cudaMemcpy(t_a.as<double>(), a, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(t_b.as<double>(), b, sizeof(double) * n, cudaMemcpyHostToDevice));
+        arith_probe_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(kind, t_a.as<double>(), t_b.as<double>(), n, t_o.as<double>());
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpy(out, t_o.as<double>(), sizeof(double) * n * per, cudaMemcpyDeviceToHost));
+    } catch (const std::exception& ex) { return fail(ctx, TRAY_E_CUDA, ex.what()); }
+    return TRAY_OK;
+}
+
 int tray_linear_to_srgb(tray_ctx* ctx, const double* x, int32_t n, uint8_t* out) {
     if (!ctx) return TRAY_E_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);

@@ -74,7 +74,8 @@ struct TraceArgs {
 // into a shared-memory pool, and regeneration takes them from there (measured 95.9 ms per config-2 frame). With 0 a separate
 // camera_ray_kernel makes all camera rays of the pass ahead and they travel through HBM, 64 B/path each way (97.8 ms).
 // Either way the per-sample camera code never runs on the handful of lanes whose path has just ended (101.2 ms).
-template <int TPB> constexpr size_t kGenPoolBytes = TRAY_GEN_INKERNEL ? (size_t)TPB * 64 : 0;
+constexpr unsigned kGenSlots = 32;  // camera rays a warp generates at a time (its pool: 32 slots of 64 bytes)
+template <int TPB> constexpr size_t kGenPoolBytes = TRAY_GEN_INKERNEL ? (size_t)(TPB / 32) * kGenSlots * 64 : 0;
 
 // One generated camera ray: what Tracer.RenderLines + Camera.GetRay leave behind for a sample (ray/tracer.go:133-141,
 // ray/camera.go:113-142): origin, direction and the generator state after the pixel-jitter and aperture draws.
@@ -383,6 +384,7 @@ template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
                                                        T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
     const T tmin = front_epsilon<T>();
+    const T ra = trcp(a);  // every root is divided by the same a: one reciprocal chain per ray segment (rcp_refined)
 #pragma unroll 1
     for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
         const int id = cand[k * TPB];
@@ -396,10 +398,10 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
         const T hi = best_t * a * up, lo = tmin * a * dn;
         T x = h - sq;
         bool ok = false;
-        if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+        if (x < hi && x > lo) { root = tdiv_r(x, a, ra); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
         if (!ok) {
             x = h + sq;
-            if (x < hi && x > lo) { root = tdiv(x, a); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
+            if (x < hi && x > lo) { root = tdiv_r(x, a, ra); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
         }
         if (ok) { best_t = root; best = id; }
     }
@@ -542,19 +544,24 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
             ucm = (unsigned long long)(w == -1 ? S.cl_always_last : 0xffu) << 56;
         } else {
             cbase = w * 64;
-            const unsigned ad1 = a_box1 + (unsigned)w * (4u * 48u);
-            unsigned ug = may_hit8(merge4(boxes(ad1), boxes(ad1 + 48), boxes(ad1 + 96), boxes(ad1 + 144)));
-            nboxes += 8;
+            // ONE copy of the 8-box test serves both levels (instruction-cache footprint: the trace kernel's per-segment code is
+            // at the size of the 32 KB instruction cache): first the word's 8 group boxes (gi < 0), then the 8 chunk boxes of
+            // every marked group. The branch on gi is warp-uniform.
+            unsigned adb = a_box1 + (unsigned)w * (4u * 48u);
+            unsigned ug = 0;
+            int gi = -1;
             unsigned long long cm = 0;
 #pragma unroll 1
-            while (ug) {
+            for (;;) {
+                const unsigned m8 = merge4(boxes(adb), boxes(adb + 48), boxes(adb + 96), boxes(adb + 144));
+                nboxes += 8;
+                if (gi < 0) ug = may_hit8(m8);
+                else cm |= (unsigned long long)(off ? 0xffu : (~m8 & 0xffu)) << (56 - 8 * gi);
+                if (!ug) break;
                 const int gbit = 31 - __clz(ug);
                 ug &= ~(1u << gbit);
-                const int gi = 7 - gbit;
-                const unsigned ad2 = a_box2 + (unsigned)(w * 8 + gi) * (4u * 48u);
-                const unsigned m8 = merge4(boxes(ad2), boxes(ad2 + 48), boxes(ad2 + 96), boxes(ad2 + 144));
-                cm |= (unsigned long long)(off ? 0xffu : (~m8 & 0xffu)) << (56 - 8 * gi);
-                nboxes += 8;
+                gi = 7 - gbit;
+                adb = a_box2 + (unsigned)(w * 8 + gi) * (4u * 48u);
             }
             if (!has) cm = 0;
             const unsigned lo = __reduce_or_sync(kFull, (unsigned)cm), hi = __reduce_or_sync(kFull, (unsigned)(cm >> 32));
@@ -642,7 +649,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
     ZigTables* zig = reinterpret_cast<ZigTables*>(smem_raw + geo_bytes);
     uint16_t* cand_all = reinterpret_cast<uint16_t*>(smem_raw + geo_bytes + sizeof(ZigTables));
     const size_t pool_off = (geo_bytes + sizeof(ZigTables) + (size_t)kCand * TPB * sizeof(uint16_t) + 15) & ~(size_t)15;
-    CamRay* gpool = reinterpret_cast<CamRay*>(smem_raw + pool_off) + (threadIdx.x & ~31);  // this warp's 32 generated camera rays
+    CamRay* gpool = reinterpret_cast<CamRay*>(smem_raw + pool_off) + (threadIdx.x >> 5) * kGenSlots;  // this warp's generated camera rays
     RegroupBuf<TPB>* xb = reinterpret_cast<RegroupBuf<TPB>*>(smem_raw + pool_off + kGenPoolBytes<TPB>);
     const int tid = threadIdx.x;
     if (GEO == kGeoShared)
@@ -692,8 +699,8 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     pool_end = (unsigned)base + kBatch < n_samples ? (unsigned)base + kBatch : n_samples;
                 }
 #if TRAY_GEN_INKERNEL
-                if (gen_avail == 0) {  // the whole warp generates the camera rays of the next (up to) 32 samples of its batch
-                    const unsigned n = pool_end - pool_next < 32u ? pool_end - pool_next : 32u;
+                if (gen_avail == 0) {  // the whole warp generates the camera rays of the next (up to) kGenSlots samples of its batch
+                    const unsigned n = pool_end - pool_next < kGenSlots ? pool_end - pool_next : kGenSlots;
                     if ((unsigned)lane < n) {
                         Pcg g;
                         V3<double> o64, d64;
@@ -708,7 +715,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 }
                 unsigned avail = gen_avail;
                 unsigned rank = __popc(need & lt_mask);
-                if (!has && rank < avail && TRAY_CHECK(gen_first + rank < 32u)) {
+                if (!has && rank < avail && TRAY_CHECK(gen_first + rank < kGenSlots)) {
                     my_li = gen_base + gen_first + rank;
                     const double2* q = reinterpret_cast<const double2*>(gpool + gen_first + rank);
 #else
@@ -931,7 +938,8 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
             }
             if (finish) {
                 if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
-                    for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56
+#pragma unroll 1
+                    for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56 (one copy: instruction-cache footprint)
                         int id;
                         if constexpr (REGROUP) id = A.stk_g[(size_t)k * A.n_slots + slot];
                         else id = stk[k];
@@ -1293,6 +1301,20 @@ __global__ void rng_dump_kernel(int kind, unsigned long long idx, unsigned long 
         else if (kind == 3) { V3<double> v = pcg_unit_vector(r, &zig, unitvec_variant); out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z; }
         else { double x, y; pcg_in_disc(r, radius, x, y, indisc_variant); out[2 * i] = x; out[2 * i + 1] = y; }
     }
+}
+
+// Arithmetic parity probe: the device's out-of-line IEEE operations on caller-supplied operands (checked on the host against
+// its own IEEE division / square root). kind 0: div3_f64(a[i], a[i+1], a[i+2], b[i]) (3 per element, indices mod n);
+// 1: div_by_rcp(a[i], b[i], rcp_refined(b[i])); 2: sqrt_f64(a[i]); 3: div_f64(a[i], b[i]).
+__global__ void arith_probe_kernel(int kind, const double* a, const double* b, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind == 0) {
+        const V3<double> q = div3_f64(a[i], a[(i + 1) % n], a[(i + 2) % n], b[i]);
+        out[3 * i] = q.x; out[3 * i + 1] = q.y; out[3 * i + 2] = q.z;
+    } else if (kind == 1) out[i] = div_by_rcp(a[i], b[i], rcp_refined(b[i]));
+    else if (kind == 2) out[i] = sqrt_f64(a[i]);
+    else out[i] = div_f64(a[i], b[i]);
 }
 
 __global__ void srgb_kernel(const double* x, int n, const double* thr, unsigned char* out) {

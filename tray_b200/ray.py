@@ -295,6 +295,15 @@ class Context:
             return out.view(np.uint64)
         return out.reshape(n, per) if per > 1 else out
 
+    def arith_probe(self, kind, a, b):
+        """Device IEEE division / sqrt routines on given operands (kind: 0 div3, 1 shared-reciprocal division, 2 sqrt, 3 plain division)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        out = np.zeros(len(a) * (3 if kind == 0 else 1))
+        p = lambda v: v.ctypes.data_as(C.c_void_p)
+        _lib.check(self.handle, self._L.tray_arith_probe(self.handle, kind, p(a), p(b), len(a), p(out)))
+        return out.reshape(len(a), 3) if kind == 0 else out
+
     def linear_to_srgb(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         out = np.zeros(len(x), dtype=np.uint8)
