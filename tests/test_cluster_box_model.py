@@ -45,7 +45,11 @@ def cluster_tables(cx, cy, cz, r):
             c[j::2, 0], c[j::2, 1], c[j::2, 2] = b[:, 0, j], b[:, 0, 2 + j], b[:, 1, j]
             e[j::2, 0], e[j::2, 1], e[j::2, 2] = b[:, 1, 2 + j], b[:, 2, j], b[:, 2, 2 + j]
         return c, e
-    m.update(n_chunks=n_chunks, pairs=pairs, ids=ids, box2=boxes(m["off_box2"], n_chunks), box1=boxes(m["off_box1"], m["real_groups"]), r=float(rr.value))
+    words8 = (m["real_groups"] // 8 + 7) // 8 * 8  # [box0]: one box per word of 8 groups, padded to a multiple of 8 words, right after [box1]
+    off_box0 = m["off_box1"] + m["real_groups"] // 2 * 3
+    assert off_box0 + words8 // 2 * 3 == m["off_ids"]
+    m.update(n_chunks=n_chunks, pairs=pairs, ids=ids, box2=boxes(m["off_box2"], n_chunks), box1=boxes(m["off_box1"], m["real_groups"]),
+             box0=boxes(off_box0, words8), words8=words8, r=float(rr.value))
     return m
 
 
@@ -57,7 +61,7 @@ def scenes():
     yield "rich", s.cx, s.cy, s.cz, s.r
     yield "empty", [], [], [], []
     yield "one", [0.5], [1.0], [-2.0], [0.25]
-    for n in (7, 8, 9, 63, 64, 65, 200, 513, 700):
+    for n in (7, 8, 9, 63, 64, 65, 200, 513, 700, 4100, 10001):
         yield "rand%d" % n, rs.uniform(-20, 20, n), rs.uniform(0, 3, n), rs.uniform(-20, 20, n), rs.choice([0.2, 0.3, 1.5, -0.4], n)
     n = 40  # many unfilterable spheres (far away / huge) plus many large ones
     yield "far", np.r_[rs.uniform(-20, 20, n), rs.uniform(300, 900, 20)], rs.uniform(-5, 5, n + 20), rs.uniform(-20, 20, n + 20), \
@@ -80,6 +84,7 @@ def test_cluster_tables_partition_the_scene(name, cx, cy, cz, r):
     assert m["unfilterable"] == int((~filt).sum())
     c2, e2 = m["box2"]
     c1, e1 = m["box1"]
+    c0, e0 = m["box0"]   # word boxes (the level cluster_scan_big tests first)
     first_always = m["real_groups"] * 8
     for ch in range(m["n_chunks"]):
         for u in range(8):
@@ -97,7 +102,7 @@ def test_cluster_tables_partition_the_scene(name, cx, cy, cz, r):
             assert entry[3] == -F32((cx[i] * cx[i] + cy[i] * cy[i] + cz[i] * cz[i]) - r[i] * r[i])
             lo = np.array([cx[i], cy[i], cz[i]]) - abs(r[i])
             hi = np.array([cx[i], cy[i], cz[i]]) + abs(r[i])
-            for cc, ee in ((c2[ch], e2[ch]),) + (((c1[ch // 8], e1[ch // 8]),) if ch < first_always else ()):
+            for cc, ee in ((c2[ch], e2[ch]),) + (((c1[ch // 8], e1[ch // 8]), (c0[ch // 64], e0[ch // 64])) if ch < first_always else ()):
                 assert (cc.astype(np.float64) - ee.astype(np.float64) < lo).all() and (cc.astype(np.float64) + ee.astype(np.float64) > hi).all()
                 if np.isfinite(ee).all():   # (an always-chunk holding an unbounded sphere has the box "everything")
                     assert (np.abs(cc.astype(np.float64)) + ee.astype(np.float64) <= m["r"]).all()
@@ -107,6 +112,9 @@ def test_cluster_tables_partition_the_scene(name, cx, cy, cz, r):
     for g in range(m["real_groups"]):
         if g not in used_groups:
             assert (e1[g] == -np.inf).all()
+    for wd in range(m["words8"]):
+        if wd >= m["real_groups"] // 8 or not any(g in used_groups for g in range(8 * wd, 8 * wd + 8)):
+            assert (e0[wd] == -np.inf).all(), "an empty or padding word can never be hit"
     if m["always_groups"]:
         last = [ch for ch in range(first_always + 8 * (m["always_groups"] - 1), m["n_chunks"]) if (ids[ch] < n).any()]
         assert m["always_last"] == sum(0x80 >> (ch % 8) for ch in last)

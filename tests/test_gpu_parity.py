@@ -342,19 +342,21 @@ def test_bvh_ties_nested_and_degenerate_scenes(ctx, O):
             assert np.array_equal(img, ref) and t.Stats["segments"] == st["segments"], (name, accel)
 
 
-# ---- large scene, BASELINE config 4 shape at a small image: BVH (automatic above 2048 spheres) and linear scan ------
+# ---- large scene, BASELINE config 4 shape at a small image: three-level clusters (automatic above 2048 spheres), BVH and linear scan ------
 def test_dense_scene_10k_spheres(ctx, O):
     scene = ray.RichScene(rand.New(2), half=50)
     assert 9900 < len(scene.Objects) < 10005
     ref, _, st = O.render(O.rich_scene(2, 50), O.camera_init(48, 27, **O.RICH_CAMERA),
                           O.make_params(48, 27, spp=2, max_depth=12, seed=2, num_workers=8, stream_mode=1, fma_mode=0))
-    for accel in (ray.ACCEL_AUTO, ray.ACCEL_BRUTE):
+    for accel in (ray.ACCEL_AUTO, ray.ACCEL_CLUSTER, ray.ACCEL_BVH, ray.ACCEL_BRUTE):
         t = tracer(48, 27, 2, 12)
         t.Accel = accel
         img = t.Render(scene).copy()
         assert np.array_equal(img, ref) and t.Stats["segments"] == st["segments"], accel
-        if accel == ray.ACCEL_AUTO:
+        if accel != ray.ACCEL_BRUTE:
             assert t.Stats["sphere_tests"] < st["sphere_tests"] / 50
+        if accel in (ray.ACCEL_AUTO, ray.ACCEL_CLUSTER):
+            assert t.Stats["box_tests"] > 0  # the cluster walk ran (cluster_scan_big), not the per-lane BVH
 
 
 # ---- full-size properties (BASELINE config 2: 1920x1080, 64 rays/pixel, depth 50) ---------------------------
@@ -507,7 +509,8 @@ def _random_scene(rs, n, scale, shift):
 
 
 @pytest.mark.parametrize("seed,n,scale,shift", [(1, 40, 1.0, 0.0), (2, 150, 5.0, 3.0), (3, 500, 30.0, -100.0), (4, 60, 200.0, 0.0),
-                                                 (5, 30, 1e-3, 0.0), (6, 90, 3.0, 250.0), (7, 700, 12.0, 0.0), (8, 25, 1e4, 0.0)])
+                                                 (5, 30, 1e-3, 0.0), (6, 90, 3.0, 250.0), (7, 700, 12.0, 0.0), (8, 25, 1e4, 0.0),
+                                                 (9, 1800, 12.0, 0.0), (10, 4000, 40.0, 50.0), (11, 9000, 25.0, 0.0)])  # (the last three: three-level walk, tables in global memory)
 def test_prefilter_never_changes_a_result_on_random_scenes(ctx, seed, n, scale, shift):
     """Images, linear-HDR means and segment counts of the default kernel (two-level clusters + pre-filter), of the linear
     pre-filter scan in the plain, regroup and wavefront layouts and of the BVH must equal the all-fp64 linear scan bit for bit, whatever the scene looks like --

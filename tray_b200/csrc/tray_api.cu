@@ -107,7 +107,7 @@ struct Device {
     float4* fpair = nullptr; float filt_mc = 0, filt_r2max = 0;
     // two-level cluster tables (cluster_scan)
     float4* cl_blob = nullptr; size_t cap_cl_blob = 0;
-    int cl_blob_f4 = 0, cl_off_box2 = 0, cl_off_box1 = 0, cl_off_ids = 0, cl_real_groups = 0, cl_always_groups = 0;
+    int cl_blob_f4 = 0, cl_off_box2 = 0, cl_off_box1 = 0, cl_off_box0 = 0, cl_off_ids = 0, cl_real_groups = 0, cl_always_groups = 0;
     unsigned cl_always_last = 0; float cl_r = 0; bool cl_present = false;
     BvhNode* bvh = nullptr; int* bvh_leaf_ids = nullptr; int* bvh_always = nullptr; int bvh_n_always = 0; double bvh_extent = 0;
     bool bvh_present = false;
@@ -236,7 +236,7 @@ void free_scene(Device& d) {
 template <typename T>
 void fill_cluster(DevScene<T>& s, const Device& d) {
     s.cl_blob = d.cl_present ? d.cl_blob : nullptr; s.cl_blob_f4 = d.cl_blob_f4;
-    s.cl_off_box2 = d.cl_off_box2; s.cl_off_box1 = d.cl_off_box1; s.cl_off_ids = d.cl_off_ids;
+    s.cl_off_box2 = d.cl_off_box2; s.cl_off_box1 = d.cl_off_box1; s.cl_off_box0 = d.cl_off_box0; s.cl_off_ids = d.cl_off_ids;
     s.cl_real_groups = d.cl_real_groups; s.cl_always_groups = d.cl_always_groups; s.cl_always_last = d.cl_always_last; s.cl_r = d.cl_r;
 }
 template <typename T> DevScene<T> dev_scene(const tray_ctx* ctx, const Device& d);
@@ -285,6 +285,7 @@ DevCamera dev_camera(const tray_camera* c, int indisc_variant = 0) {
 constexpr int kTPB = TRAY_TPB;        // threads per CTA of the trace kernel
 constexpr int kMinBlocks = TRAY_MINB; // resident CTAs per SM the register allocation targets
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr int kSmemClusterMax = 2048;  // up to here the cluster tables are staged into shared memory (two levels); above: cluster_scan_big
 
 // Regroup layout (pre-filter kernel only): same launch shape, plus the exchange area in shared memory and the
 // attenuation stacks in global memory (max_depth x lanes x 2 bytes, L2 resident).
@@ -318,7 +319,7 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 #ifndef TRAY_CLUSTER_MINB
 #define TRAY_CLUSTER_MINB 4
 #endif
-    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : (GEO == kGeoCluster ? TRAY_CLUSTER_MINB : kMinBlocks);
+    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : ((GEO == kGeoCluster || GEO == kGeoClusterBig) ? TRAY_CLUSTER_MINB : kMinBlocks);
     auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
     int bps = 0;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -344,10 +345,15 @@ struct TraceLaunch {
                 return;
             }
         }
-        if (filter && use == kUseCluster && S.cl_blob && (size_t)S.cl_blob_f4 * 16 + tail <= kSmemBudget) {
+        if (filter && use == kUseCluster && S.cl_blob && S.n <= kSmemClusterMax && (size_t)S.cl_blob_f4 * 16 + tail <= kSmemBudget) {
             if (regroup) { launch_trace_regroup<T, FMA, kGeoCluster>(d, A, S, (size_t)S.cl_blob_f4 * 16 + tail); return; }
             GeoArg<T, kGeoCluster> none{};
             launch_trace_geo<T, FMA, kGeoCluster>(d, A, S, none, (size_t)S.cl_blob_f4 * 16 + tail);
+            return;
+        }
+        if (filter && use == kUseCluster && S.cl_blob) {  // large scene: three levels, tables in global memory (plain layout only)
+            GeoArg<T, kGeoClusterBig> none{};
+            launch_trace_geo<T, FMA, kGeoClusterBig>(d, A, S, none, tail);
             return;
         }
         if (filter && S.fpair && (size_t)S.n_pad * 16 + tail <= kSmemBudget) {
@@ -421,14 +427,14 @@ int launch_trace_wavefront(Device& d, const TraceArgs& A, const DevScene<double>
 #endif
 // AUTO: two-level clusters while the scene is small enough for their tables (and the filter can bound nearly all of it),
 // the per-lane BVH above; BRUTE: the linear scan in the reference's Scene.Hit order.
-constexpr int kAutoClusterMax = 2048, kAutoClusterUnfilterable = 64;
+constexpr int kAutoClusterMax = 32768, kAutoClusterUnfilterable = 64;
 int closest_hit_structure(const tray_ctx* ctx, const Device& d, int accel) {
     const bool cluster_ok = d.cl_present;
     if (accel == TRAY_ACCEL_BVH) return kUseBvh;
     if (accel == TRAY_ACCEL_CLUSTER) return cluster_ok ? kUseCluster : kUseLinear;
     if (accel == TRAY_ACCEL_BRUTE) return kUseLinear;
     if (cluster_ok && d.n <= kAutoClusterMax && ctx->cluster_unfilterable <= kAutoClusterUnfilterable) return kUseCluster;
-    return d.n > kAutoClusterMax ? kUseBvh : kUseLinear;
+    return d.n > kSmemClusterMax ? kUseBvh : kUseLinear;
 }
 
 // The wavefront layout exists for the strict fp64 linear scan only; everything else runs the megakernel.
@@ -588,7 +594,7 @@ bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<in
 // when there are only a few, spheres much larger than the rest go into "always" groups that every ray scans.
 struct ClusterHost {
     std::vector<float4> blob;
-    int off_box2 = 0, off_box1 = 0, off_ids = 0, real_groups = 0, always_groups = 0;
+    int off_box2 = 0, off_box1 = 0, off_box0 = 0, off_ids = 0, real_groups = 0, always_groups = 0, words8 = 0;
     unsigned always_last = 0;
     float r = 0;
     int unfilterable = 0;
@@ -642,25 +648,27 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
         if (!big.empty() && always.size() + big.size() <= 16) { always.insert(always.end(), big.begin(), big.end()); pool = rest; }
     }
     std::sort(always.begin(), always.end());
-    // slot order: real groups (chunks of the pool, group by group), then the always-groups
-    std::vector<std::pair<int, int>> groups, chunks;
-    cluster_split(sc, pool, 0, (int)pool.size(), 64, groups);
+    // slot order: real groups (chunks of the pool, group by group, 8 group slots per word of 512 spheres), then the always-groups
+    std::vector<std::pair<int, int>> words, groups, chunks;
+    cluster_split(sc, pool, 0, (int)pool.size(), 512, words);
     std::vector<std::vector<int>> chunk_ids;   // [chunk] -> sphere ids (ascending); 8 chunk slots per group
-    std::vector<int> group_first_chunk;
-    for (auto& g : groups) {
-        chunks.clear();
-        cluster_split(sc, pool, g.first, g.second, 8, chunks);
-        group_first_chunk.push_back((int)chunk_ids.size());
-        for (auto& c : chunks) {
-            std::vector<int> v(pool.begin() + c.first, pool.begin() + c.first + c.second);
-            std::sort(v.begin(), v.end());
-            chunk_ids.push_back(v);
+    for (auto& w : words) {
+        groups.clear();
+        cluster_split(sc, pool, w.first, w.second, 64, groups);
+        for (auto& g : groups) {
+            chunks.clear();
+            cluster_split(sc, pool, g.first, g.second, 8, chunks);
+            for (auto& c : chunks) {
+                std::vector<int> v(pool.begin() + c.first, pool.begin() + c.first + c.second);
+                std::sort(v.begin(), v.end());
+                chunk_ids.push_back(v);
+            }
+            while (chunk_ids.size() % 8) chunk_ids.push_back({});
         }
-        while (chunk_ids.size() % 8) chunk_ids.push_back({});
+        while (chunk_ids.size() % 64) chunk_ids.push_back({});
     }
-    const int used_real_groups = (int)groups.size();
-    H.real_groups = (used_real_groups + 7) / 8 * 8;
-    while ((int)chunk_ids.size() < H.real_groups * 8) chunk_ids.push_back({});
+    H.real_groups = (int)words.size() * 8;
+    H.words8 = ((int)words.size() + 7) / 8 * 8;
     H.always_groups = ((int)always.size() + 63) / 64;
     for (size_t k = 0; k < always.size(); k += 8)
         chunk_ids.push_back(std::vector<int>(always.begin() + k, always.begin() + std::min(always.size(), k + 8)));
@@ -683,9 +691,9 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
         }
         b.empty = false;
     };
-    std::vector<Box> box2(n_chunks), box1(n_groups_all);
+    std::vector<Box> box2(n_chunks), box1(n_groups_all), box0(H.words8 + 1);
     for (int c = 0; c < n_chunks; c++)
-        for (int i : chunk_ids[c]) { grow_box(box2[c], i); grow_box(box1[c / 8], i); }
+        for (int i : chunk_ids[c]) { grow_box(box2[c], i); grow_box(box1[c / 8], i); if (c / 64 < (int)words.size()) grow_box(box0[c / 64], i); }
     float rmax = 0.f;
     auto emit = [&](const Box* b0, const Box* b1, float4* out) {  // one pair of boxes -> three float4 (centre, half extent)
         float c[2][3], e[2][3];
@@ -703,8 +711,10 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
         out[1] = make_float4(c[0][2], c[1][2], e[0][0], e[1][0]);
         out[2] = make_float4(e[0][1], e[1][1], e[0][2], e[1][2]);
     };
-    const int f4_pairs = n_chunks * 8, f4_box2 = n_chunks / 2 * 3, f4_box1 = H.real_groups / 2 * 3, f4_ids = (n_chunks * 8 * 2 + 15) / 16;
-    H.off_box2 = f4_pairs; H.off_box1 = H.off_box2 + f4_box2; H.off_ids = H.off_box1 + f4_box1;
+    // [pairs][box2: one box per chunk][box1: per group][box0: per word of 8 groups, padded to a multiple of 8 words][ids]
+    const int f4_pairs = n_chunks * 8, f4_box2 = n_chunks / 2 * 3, f4_box1 = H.real_groups / 2 * 3, f4_box0 = H.words8 / 2 * 3,
+              f4_ids = (n_chunks * 8 * 2 + 15) / 16;
+    H.off_box2 = f4_pairs; H.off_box1 = H.off_box2 + f4_box2; H.off_box0 = H.off_box1 + f4_box1; H.off_ids = H.off_box0 + f4_box0;
     H.blob.assign((size_t)H.off_ids + f4_ids + 8, make_float4(0, 0, 0, 0));  // + slack: nothing reads past it, kept for safety
     uint16_t* ids16 = reinterpret_cast<uint16_t*>(H.blob.data() + H.off_ids);
     float mc = 0.f;
@@ -727,13 +737,13 @@ ClusterHost build_clusters(const tray_scene_desc* sc, int pad_id) {
         }
     }
     for (int c = 0; c < n_chunks; c += 2) emit(&box2[c], &box2[c + 1], H.blob.data() + H.off_box2 + c / 2 * 3);
-    for (int g = 0; g < H.real_groups; g += 2)
-        emit(g < used_real_groups ? &box1[g] : nullptr, g + 1 < used_real_groups ? &box1[g + 1] : nullptr, H.blob.data() + H.off_box1 + g / 2 * 3);
+    for (int g = 0; g < H.real_groups; g += 2) emit(&box1[g], &box1[g + 1], H.blob.data() + H.off_box1 + g / 2 * 3);  // (empty group slots: never hit)
+    for (int w = 0; w < H.words8; w += 2) emit(&box0[w], &box0[w + 1], H.blob.data() + H.off_box0 + w / 2 * 3);
     H.r = std::max(rmax, mc) * 1.0000002f;
     return H;
 }
 
-constexpr int kClusterMaxSpheres = 4096;  // 64 groups x 8 chunks x 8 spheres: 8 words of group boxes per segment at most
+constexpr int kClusterMaxSpheres = 32768;  // 64 words x 8 groups x 8 chunks x 8 spheres (the marked words of a segment are one 64-bit mask; slot ids are 16 bits)
 constexpr int kBandRows = 1;  // rows per band of the tile split: single rows balance best (2160 rows over 8 shards: 270 each; 8-row bands gave 33 or 34 bands and 0.94 scaling efficiency at 8 GPUs)
 // Scratch per pass, in samples (x24 bytes), whole pixels per pass: at least this much, more when the device has the room
 // (tray_render sizes a pass from cudaMemGetInfo so that a device's whole share is one pass when it fits).
@@ -925,7 +935,7 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             if (use_clusters) {
                 grow(d.cl_blob, d.cap_cl_blob, clh.blob.size());
                 CK(cudaMemcpy(d.cl_blob, clh.blob.data(), sizeof(float4) * clh.blob.size(), cudaMemcpyHostToDevice));
-                d.cl_blob_f4 = (int)clh.blob.size(); d.cl_off_box2 = clh.off_box2; d.cl_off_box1 = clh.off_box1; d.cl_off_ids = clh.off_ids;
+                d.cl_blob_f4 = (int)clh.blob.size(); d.cl_off_box2 = clh.off_box2; d.cl_off_box1 = clh.off_box1; d.cl_off_box0 = clh.off_box0; d.cl_off_ids = clh.off_ids;
                 d.cl_real_groups = clh.real_groups; d.cl_always_groups = clh.always_groups; d.cl_always_last = clh.always_last; d.cl_r = clh.r;
                 d.cl_present = true;
             }

@@ -133,7 +133,8 @@ template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_fl
 //   kGeoFilter : linear scan behind the exact fp32 pair pre-filter (filter_scan).
 //   kGeoBVH    : per-lane BVH traversal (large scenes).
 //   kGeoCluster: two-level boxes over chunks of 8 spheres, warp-uniform, then the pair pre-filter on the marked chunks (cluster_scan).
-enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3, kGeoBVH = 4, kGeoCluster = 5 };
+//   kGeoClusterBig: the same walk with a third level of boxes on top and the tables in global memory (cluster_scan_big).
+enum { kGeoGlobal = 0, kGeoShared = 1, kGeoParam = 2, kGeoFilter = 3, kGeoBVH = 4, kGeoCluster = 5, kGeoClusterBig = 6 };
 #ifndef TRAY_PARAM_GEO
 #define TRAY_PARAM_GEO 0
 #endif
@@ -615,6 +616,192 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     }
 }
 
+// The cluster scan for scenes whose tables do not fit shared memory (kGeoClusterBig: 2049 .. 32768 spheres, BASELINE config 4):
+// same structure and the same tests as cluster_scan, with
+//   * the tables read from GLOBAL memory through the read-only path -- every load of the walk is warp-uniform (one L1
+//     transaction, broadcast), the hot part of the 200 KB of tables stays in L1/L2 --, and
+//   * a third level on top: one box per WORD of 8 groups (512 slots). The word boxes are tested first, 8 at a time, the
+//     warp's union of marked words is one 64-bit mask, and only marked words run the group -> chunk -> pair-filter walk.
+//     (cluster_scan tests the group boxes of every word: 8 box tests per 512 spheres for every ray.)
+// Conservativeness is that of cluster_scan: a box of any level contains the boxes below it (build_clusters), the slab test
+// and its bound are the same code. Results are bit-identical to the linear scan (GPU tests on 10 001 spheres).
+template <typename T, bool FMA, int TPB>
+__device__ __forceinline__ void cluster_scan_big(const DevScene<T>& S, const typename Vec4T<T>::type* __restrict__ ggeo,
+                                                 uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a, T udx, T udy, T udz,
+                                                 T& best_t, int& best, int& ncand, unsigned& nchunks, unsigned& nboxes,
+                                                 const volatile double* parked = nullptr) {
+    // ---- per-ray constants: as cluster_scan ----
+    const float u32 = 5.9604645e-8f;
+    const double ddx = (double)udx, ddy = (double)udy, ddz = (double)udz;
+    const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+    float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+    const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+    const float R = S.cl_r + mo;
+    float eh = 17.5f * u32 * R;
+    float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+                         ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));
+    const bool off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
+    if (off) { noot = __int_as_float(0x7f800000); eh = 0.0f; }
+    ndo += eh;
+    const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
+    const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
+    const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
+    const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
+    auto rcp = [](float d) {
+        const float lim = 8.6736174e-19f;  // 2^-60
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(d) < lim ? copysignf(lim, d) : d));
+        return r;
+    };
+    const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
+    const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
+    const float ks = 16.0f * u32 * R;
+    const float2 IX = make_float2(ix, ix), IY = make_float2(iy, iy), IZ = make_float2(iz, iz);
+    const float2 NQX = make_float2(nqx, nqx), NQY = make_float2(nqy, nqy), NQZ = make_float2(nqz, nqz);
+    const float2 AX = make_float2(fabsf(ix), fabsf(ix)), AY = make_float2(fabsf(iy), fabsf(iy)), AZ = make_float2(fabsf(iz), fabsf(iz));
+    const float2 SX = make_float2(ks * fabsf(ix), ks * fabsf(ix)), SY = make_float2(ks * fabsf(iy), ks * fabsf(iy)),
+                 SZ = make_float2(ks * fabsf(iz), ks * fabsf(iz));
+
+    const float4* __restrict__ gb = S.cl_blob;
+    auto ldg4 = [&](float4& v, unsigned idx) {  // idx: float4 index into the blob (warp-uniform)
+        if (!TRAY_CHECK(idx < (unsigned)S.cl_blob_f4)) { v = make_float4(0, 0, 0, 0); return; }
+        v = __ldg(gb + idx);
+    };
+    auto pair = [&](const float4& g0, const float4& g1) -> unsigned {  // two spheres: 8 packed instructions (see filter_scan)
+        const float2 cx = make_float2(g0.x, g0.y), cy = make_float2(g0.z, g0.w), cz = make_float2(g1.x, g1.y);
+        float2 h = __ffma2_rn(Dx, cx, __ffma2_rn(Dy, cy, __ffma2_rn(Dz, cz, NDO)));
+        float2 nko = __fadd2_rn(make_float2(g1.z, g1.w), NOOT);
+        float2 nc = __ffma2_rn(Px, cx, __ffma2_rn(Py, cy, __ffma2_rn(Pz, cz, nko)));
+        float2 v1 = __ffma2_rn(h, h, nc);
+        int mx = __float_as_int(v1.x) | (__float_as_int(h.x) & __float_as_int(nc.x));
+        int my = __float_as_int(v1.y) | (__float_as_int(h.y) & __float_as_int(nc.y));
+        return __funnelshift_l((unsigned)my, (unsigned)mx >> 31, 1);
+    };
+    auto merge4 = [](unsigned p0, unsigned p1, unsigned p2, unsigned p3) -> unsigned { return (((p0 << 2) | p1) << 4) | ((p2 << 2) | p3); };
+    auto boxes = [&](unsigned idx) -> unsigned {  // two boxes (three float4), see cluster_scan
+        float4 b0, b1, b2;
+        ldg4(b0, idx); ldg4(b1, idx + 1); ldg4(b2, idx + 2);
+        const float2 ax = __ffma2_rn(make_float2(b0.x, b0.y), IX, NQX), ay = __ffma2_rn(make_float2(b0.z, b0.w), IY, NQY),
+                     az = __ffma2_rn(make_float2(b1.x, b1.y), IZ, NQZ);
+        const float2 bx = __ffma2_rn(make_float2(b1.z, b1.w), AX, SX), by = __ffma2_rn(make_float2(b2.x, b2.y), AY, SY),
+                     bz = __ffma2_rn(make_float2(b2.z, b2.w), AZ, SZ);
+        const float2 nx = __fadd2_rn(ax, make_float2(-bx.x, -bx.y)), ny = __fadd2_rn(ay, make_float2(-by.x, -by.y)),
+                     nz = __fadd2_rn(az, make_float2(-bz.x, -bz.y));
+        const float2 fx = __fadd2_rn(ax, bx), fy = __fadd2_rn(ay, by), fz = __fadd2_rn(az, bz);
+        const float tn0 = fmaxf(fmaxf(nx.x, ny.x), nz.x), tf0 = fminf(fminf(fx.x, fy.x), fz.x);
+        const float tn1 = fmaxf(fmaxf(nx.y, ny.y), nz.y), tf1 = fminf(fminf(fx.y, fy.y), fz.y);
+        return __funnelshift_l((unsigned)(__float_as_int(tf1 - tn1) | __float_as_int(tf1)),
+                               (unsigned)(__float_as_int(tf0 - tn0) | __float_as_int(tf0)) >> 31, 1);
+    };
+    auto may_hit8 = [&](unsigned mask) -> unsigned {
+        unsigned hit = off ? 0xffu : (~mask & 0xffu);
+        if (!has) hit = 0u;
+        return __reduce_or_sync(kFull, hit);
+    };
+    const uint16_t* __restrict__ gids = reinterpret_cast<const uint16_t*>(gb + S.cl_off_ids);
+    const int n_always = S.cl_always_groups, n_words = S.cl_real_groups >> 3;
+    // The walk is a warp-uniform state machine around ONE copy of the 8-box test and ONE copy of the chunk loop:
+    //   kL0: 8 word boxes -> uw (marked words, bit 63-w)        kL1: the 8 group boxes of word w -> ug
+    //   kL2: the 8 chunk boxes of group gi of word w -> cm      kNextGroup / kNextWord: bookkeeping, no tests
+    //   kChunks: the marked chunks (ucm) of the current word through the pair pre-filter
+    // Always-words (spheres outside the filter's range, very large ones) are scanned by every ray, after level 0.
+    enum { kL0 = 0, kL1 = 1, kL2 = 2, kNextGroup = 3, kNextWord = 4, kChunks = 5 };
+    const int n_oct0 = (n_words + 7) >> 3;
+    unsigned long long uw = 0, cm = 0, ucm = 0;
+    unsigned ug = 0, adb = (unsigned)S.cl_off_box0;
+    int st = n_oct0 > 0 ? kL0 : kNextWord, j0 = 0, w = 0, gi = 0, cbase = 0, wa = -n_always;
+#pragma unroll 1
+    for (;;) {
+        if (st <= kL2) {
+            const unsigned m8 = merge4(boxes(adb), boxes(adb + 3), boxes(adb + 6), boxes(adb + 9));
+            nboxes += 8;
+            if (st == kL0) {
+                uw |= (unsigned long long)may_hit8(m8) << (56 - 8 * j0);
+                j0++;
+                if (j0 < n_oct0) { adb += 12; continue; }
+                uw &= ~0ull << (64 - n_words);   // padding words (and "everything" of a far-out ray) stay inside the tables
+                st = kNextWord;
+            } else if (st == kL1) {
+                ug = may_hit8(m8);
+                cm = 0;
+                st = kNextGroup;
+            } else {
+                cm |= (unsigned long long)(off ? 0xffu : (~m8 & 0xffu)) << (56 - 8 * gi);
+                st = kNextGroup;
+            }
+        }
+        if (st == kNextGroup) {
+            if (ug) {
+                const int gbit = 31 - __clz(ug);
+                ug &= ~(1u << gbit);
+                gi = 7 - gbit;
+                adb = (unsigned)S.cl_off_box2 + (unsigned)(w * 8 + gi) * 12u;
+                st = kL2;
+                continue;
+            }
+            if (!has) cm = 0;
+            const unsigned lo = __reduce_or_sync(kFull, (unsigned)cm), hi = __reduce_or_sync(kFull, (unsigned)(cm >> 32));
+            ucm = ((unsigned long long)hi << 32) | lo;
+            cbase = w * 64;
+            st = ucm ? kChunks : kNextWord;
+        }
+        if (st == kNextWord) {
+            if (wa < 0) {
+                cbase = (S.cl_real_groups + (wa + n_always)) * 8;
+                ucm = (unsigned long long)(wa == -1 ? S.cl_always_last : 0xffu) << 56;
+                wa++;
+                if (ucm == 0) continue;
+            } else if (uw) {
+                w = __clzll((long long)uw);
+                uw &= ~(0x8000000000000000ull >> w);
+                adb = (unsigned)S.cl_off_box1 + (unsigned)w * 12u;
+                st = kL1;
+                continue;
+            } else break;
+        }
+        st = kNextWord;
+        // ---- the marked chunks of this word through the pair pre-filter (software-pipelined by half chunks) ----
+        int pos = __clzll((long long)ucm);
+        unsigned ad = (unsigned)(cbase + pos) * 8u;
+        float4 a0, a1, a2, a3, b0, b1, b2, b3;
+        ldg4(a0, ad); ldg4(a1, ad + 1); ldg4(a2, ad + 2); ldg4(a3, ad + 3);
+#pragma unroll 1
+        for (;;) {
+            ldg4(b0, ad + 4); ldg4(b1, ad + 5); ldg4(b2, ad + 6); ldg4(b3, ad + 7);
+            const unsigned long long rest = ucm & ~(0x8000000000000000ull >> pos);
+            const unsigned p0 = pair(a0, a1), p1 = pair(a2, a3);
+            const int npos = rest ? __clzll((long long)rest) : pos;
+            const unsigned nad = (unsigned)(cbase + npos) * 8u;
+            ldg4(a0, nad); ldg4(a1, nad + 1); ldg4(a2, nad + 2); ldg4(a3, nad + 3);
+            const unsigned mask = merge4(p0, p1, pair(b0, b1), pair(b2, b3));
+            nchunks++;
+            unsigned m = has ? (~mask & 0xffu) : 0u;  // 1 = must be tested exactly
+            if (m) {
+                const int chunk = cbase + pos;
+                if (ncand > kCand - 8) {  // list about to overflow (rare): run the exact test on what is queued
+                    T fx_ = ox, fy_ = oy, fz_ = oz, gx_ = dx, gy_ = dy, gz_ = dz;
+                    if (parked) {
+                        fx_ = T(parked[0]); fy_ = T(parked[TPB]); fz_ = T(parked[2 * TPB]);
+                        gx_ = T(parked[3 * TPB]); gy_ = T(parked[4 * TPB]); gz_ = T(parked[5 * TPB]);
+                    }
+                    const BestHit<T> bh = flush_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, fx_, fy_, fz_, gx_, gy_, gz_, best_t, best);
+                    best_t = bh.t; best = bh.id;
+                    ncand = 0;
+                }
+                do {  // bit 7-u <-> slot chunk*8+u
+                    const int bit = 31 - __clz(m);
+                    if (TRAY_CHECK(ncand < kCand && chunk >= 0 && chunk * 8 + 7 - bit < (S.cl_off_box2 >> 3) * 8))
+                        cand[ncand * TPB] = gids[chunk * 8 + 7 - bit];
+                    ncand++;
+                    m &= ~(1u << bit);
+                } while (m);
+            }
+            if (!rest) break;
+            ucm = rest; pos = npos; ad = nad;
+        }
+    }
+}
+
 // Exchange area of the regroup layout (one per CTA, shared memory): the path state of every lane, SoA.
 template <int TPB>
 struct RegroupBuf {
@@ -763,7 +950,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         __shared__ int s_parki[3][TPB];
         volatile double* pk = &s_park[0][tid];
         volatile int* pki = &s_parki[0][tid];
-        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster) && !REGROUP;
+        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP;
         if constexpr (kPark) {
             pk[0] = (double)O.x; pk[TPB] = (double)O.y; pk[2 * TPB] = (double)O.z;
             pk[3 * TPB] = (double)D.x; pk[4 * TPB] = (double)D.y; pk[5 * TPB] = (double)D.z;
@@ -784,12 +971,13 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         if constexpr (GEO == kGeoBVH) {
             bvh_closest_hit<T, FMA>(S, ggeo, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ntests_blk);
             if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
-        } else if constexpr (GEO == kGeoFilter || GEO == kGeoCluster) {
+        } else if constexpr (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) {
             unsigned nchunks = 0, nboxes = 0;
             (void)nchunks; (void)nboxes;
 #if TRAY_PARK_STATE
             if constexpr (kPark) {
                 if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pk);
+                else if constexpr (GEO == kGeoClusterBig) cluster_scan_big<T, FMA, TPB>(S, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pk);
                 else
                 filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pk);
                 ox = T(pk[0]); oy = T(pk[TPB]); oz = T(pk[2 * TPB]); dx = T(pk[3 * TPB]); dy = T(pk[4 * TPB]); dz = T(pk[5 * TPB]);
@@ -802,9 +990,10 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
 #endif
             {
                 if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes);
+                else if constexpr (GEO == kGeoClusterBig) cluster_scan_big<T, FMA, TPB>(S, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes);
                 else filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev);
             }
-            if constexpr (GEO == kGeoCluster) {
+            if constexpr (GEO == kGeoCluster || GEO == kGeoClusterBig) {
                 if (has) { ntests_blk += 8u * nchunks; nbox_blk += nboxes; }
                 if (ntests_blk > 0x40000000u) { ntests += ntests_blk; ntests_blk = 0; }
                 if (nbox_blk > 0x40000000u) { nbox += nbox_blk; nbox_blk = 0; }
@@ -831,7 +1020,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
             mask_prev = mask;
         }
         }
-        if constexpr (GEO == kGeoCluster) {
+        if constexpr (GEO == kGeoCluster || GEO == kGeoClusterBig) {
             resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
         } else {
             if (mask_prev)
