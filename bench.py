@@ -366,6 +366,12 @@ def run_ours(args):
     clocks = sampler.stop()
     dev_ms, trace_ms, launches, segments, paths = m["ms"], m["trace_ms"], m["launches"], m["segments"], m["paths"]
     trace_launches, sphere_tests, box_tests, exchange_ms = m["trace_launches"], m["sphere_tests"], m["box_tests"], m["exchange_ms"]
+    per_rank = None
+    if world > 1:  # every rank's own device time (ms per step: all kernels | trace kernel): where the max over ranks comes from
+        t = torch.tensor([dev_ms / args.steps, trace_ms / args.steps], dtype=torch.float64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        per_rank = {"ms_per_step": [round(float(x[0]), 3) for x in g], "trace_kernel_ms": [round(float(x[1]), 3) for x in g]}
     dev_ms = max_over_ranks(dev_ms)
     all_paths = sum_over_ranks(paths)
     all_segments = sum_over_ranks(segments)
@@ -670,6 +676,8 @@ def run_ours(args):
                          "note": "compute/latency-bound: HBM traffic is ~30 B/path (sample colour out); tensor cores do not apply"},
             "segments_per_path": all_segments / all_paths,
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         if split_samples:
             line["exchange"] = {"collective": "NCCL reduce(sum) to rank 0 + resolve", "bytes": int(w) * h * 24, "ms_per_step": exchange_ms / args.steps,
                                 "note": "fp64 colour sums (w*h*3 doubles) reduced in place on the library's device buffer; rank 0's time"}

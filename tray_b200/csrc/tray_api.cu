@@ -1128,11 +1128,16 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                 // One pass per device whenever its scratch (24 B per sample) fits in a share of the free memory: a pass ends with a
                 // tail in which the SMs run dry one by one, so two passes cost two tails (config 3 on 8 GPUs: 265 M samples per rank).
                 unsigned long long pass_samples = kPassSamples;
-                if (n_pixels * (unsigned long long)spp_local > pass_samples) {
-                    size_t free_b = 0, total_b = 0;
-                    CK(cudaMemGetInfo(&free_b, &total_b));
-                    const unsigned long long fit = (unsigned long long)(0.45 * (double)(free_b + d.scratch_cap * sizeof(double))) / 24ull;
-                    pass_samples = std::max(pass_samples, std::min(fit, 0xfff00000ull));  // (sample indices of a pass are 32-bit)
+                const unsigned long long share = n_pixels * (unsigned long long)spp_local;
+                if (share > pass_samples) {
+                    if (share * 3ull <= (unsigned long long)d.scratch_cap && share <= 0xfff00000ull) {
+                        pass_samples = share;  // the scratch of an earlier render already holds the whole share: no driver query
+                    } else {
+                        size_t free_b = 0, total_b = 0;
+                        CK(cudaMemGetInfo(&free_b, &total_b));  // (milliseconds on a 180 GB device: only when the scratch has to grow)
+                        const unsigned long long fit = (unsigned long long)(0.45 * (double)(free_b + d.scratch_cap * sizeof(double))) / 24ull;
+                        pass_samples = std::max(pass_samples, std::min(fit, 0xfff00000ull));  // (sample indices of a pass are 32-bit)
+                    }
                 }
                 unsigned long long px_per_pass = std::max<unsigned long long>(1, pass_samples / (unsigned)spp_local);
                 px_per_pass = std::min(px_per_pass, n_pixels);
@@ -1144,6 +1149,7 @@ int tray_render(tray_ctx* ctx, const tray_camera* cam, const tray_params* p, uin
                     CK(cudaMalloc(&d.counters, sizeof(unsigned long long) * n_pass));
                     d.counters_cap = n_pass;
                 }
+                CK(cudaEventRecord(d.ev_begin, d.stream));  // (again: the device time of a render starts after the host-side sizing above)
                 CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * n_pass, d.stream));
                 d.passes = n_pass;
                 for (int ps = 0; ps < n_pass; ps++) {

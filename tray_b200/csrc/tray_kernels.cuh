@@ -386,6 +386,9 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
                                                        T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
     const T tmin = front_epsilon<T>();
     const T ra = trcp(a);  // every root is divided by the same a: one reciprocal chain per ray segment (rcp_refined)
+    const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
+    const T lo = tmin * a * dn;
+    T hi = best_t * a * up;    // follows best_t (updated where a candidate wins)
 #pragma unroll 1
     for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
         const int id = cand[k * TPB];
@@ -395,8 +398,6 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
         if (certainly_missed(h, c, disc)) continue;
         T sq = tsqrt(disc);
-        const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
-        const T hi = best_t * a * up, lo = tmin * a * dn;
         T x = h - sq;
         bool ok = false;
         if (x < hi && x > lo) { root = tdiv_r(x, a, ra); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
@@ -404,7 +405,7 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
             x = h + sq;
             if (x < hi && x > lo) { root = tdiv_r(x, a, ra); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
         }
-        if (ok) { best_t = root; best = id; }
+        if (ok) { best_t = root; best = id; hi = root * a * up; }
     }
 }
 
