@@ -397,7 +397,7 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
         T h, c, disc, root;
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
         if (certainly_missed(h, c, disc)) continue;
-        T sq = tsqrt(disc);
+        T sq = tsqrt_hot(disc);
         T x = h - sq;
         bool ok = false;
         if (x < hi && x > lo) { root = tdiv_r(x, a, ra); ok = root > tmin && (root < best_t || (root == best_t && id < best)); }
@@ -961,7 +961,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
 #endif
         // Unit(r.Direction) is needed by the sky (objects.go:69), Metal (materials.go:29) and Dielectric (materials.go:52): computed
         // once for every lane, and BEFORE the scan, whose fp32 filters take their normalised direction from it.
-        ud = unit(D);
+        { const T l = tsqrt_hot(len2(D)); ud = div3_hot(D, l); }  // Unit(r.Direction), ray/vec3.go
 #if TRAY_PARK_STATE
         if constexpr (kPark) { pk[8 * TPB] = (double)ud.x; pk[9 * TPB] = (double)ud.y; pk[10 * TPB] = (double)ud.z; }
 #endif
