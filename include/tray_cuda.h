@@ -23,6 +23,8 @@
  *   tray_upload_frame  <- (no reference counterpart: an image the context did not render, for present / PNG / tests)
  *   tray_progress      <- Tracer.ProgressFunc      ray/tracer.go:30,126-128 (poll; deltas sum to w*h)
  *   tray_rng_dump      <- fortio.org/rand streams  ray/tracer.go:121, ray/rand.go:10-32 (parity probe)
+ *   tray_arith_probe   <- float64 `/` and math.Sqrt as Go compiles them (DIVSD / SQRTSD): Unit, SDiv ray/vec3.go:60-75,
+ *                         Sphere.Hit roots and normal ray/objects.go:90-100 (parity probe of the device's IEEE routines)
  */
 #ifndef TRAY_CUDA_H
 #define TRAY_CUDA_H

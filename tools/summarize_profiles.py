@@ -74,11 +74,12 @@ open(os.path.join(P, tag + "_trace_kernel%s_source_summary.txt" % suffix), "w").
 # time shares by what the code is for (stall samples of the function table)
 GROUPS = {
     "scan_boxes_and_prefilter": ("cluster_scan", "lambda boxes", "lambda pair", "lambda may_hit8", "lambda lds4", "lambda rcp", "sm_100_rt.hpp",
-                                 "sm_80_rt.hpp", "sm_32_intrinsics.hpp", "filter_scan", "rcp_f32"),
+                                 "sm_80_rt.hpp", "sm_32_intrinsics.hpp", "filter_scan", "rcp_f32", "lambda merge4", "lambda ldg4", "cluster_scan_big"),
     "exact_resolve": ("resolve_candidates_lex", "resolve_candidates", "sphere_terms", "flush_candidates_lex", "miss_bits", "certainly_missed", "push_candidates"),
-    "ieee_div_sqrt_fp64": ("div3_f64", "sqrt_f64", "div_f64", "tsqrt", "tdiv"),
-    "generators": ("pcg_step", "pcg_u64", "pcg_f64", "pcg_norm", "pcg_unit_vector", "go_log", "go_exp"),
-    "regenerate_camera_rays": ("camera_sample", "get_ray", "pcg_in_disc"),
+    "ieee_div_sqrt_fp64": ("div3_f64", "sqrt_f64", "div_f64", "tsqrt", "tdiv", "div3_body", "div3_hot", "rcp_refined", "div_tail", "div_tail_ok",
+                           "div_by_rcp", "tsqrt_hot", "trcp", "tdiv_r", "unit"),
+    "generators": ("pcg_step", "pcg_u64", "pcg_f64", "pcg_norm", "pcg_unit_vector", "go_log", "go_exp", "pcg_step_body", "pcg_u64_inline", "pcg_f64_pair"),
+    "regenerate_camera_rays": ("camera_sample", "get_ray", "get_ray_drawn", "pcg_in_disc"),
 }
 share = {k: 0.0 for k in GROUPS}
 share["shade_and_loop_body"] = 0.0
