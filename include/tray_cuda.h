@@ -72,11 +72,12 @@ extern "C" {
 #define TRAY_FP64_STRICT_BRUTE 3 /* as STRICT but every test in fp64 (no pre-filter): the pure FP64-pipe kernel */
 
 /* closest-hit structure. Results are identical for all of them (ties resolve to the lowest index). */
-#define TRAY_ACCEL_AUTO 0  /* two-level clusters up to 2048 spheres, BVH above */
+#define TRAY_ACCEL_AUTO 0  /* cluster boxes up to 32768 spheres (two levels in shared memory up to 2048, three levels in global memory above), BVH beyond */
 #define TRAY_ACCEL_BRUTE 1 /* linear scan of the sphere table (the reference's Scene.Hit order) */
 #define TRAY_ACCEL_BVH 2   /* small BVH (<= 4 spheres per leaf), built at upload on the host (median split) or on the device (LBVH) */
 #define TRAY_ACCEL_CLUSTER 3 /* two-level boxes over chunks of 8 spheres, tested warp-wide with a conservative fp32 slab test; only the
-                                chunks some lane of the warp may hit run the pair pre-filter (strict fp64 / fp32 modes; <= 4096 spheres) */
+                                chunks some lane of the warp may hit run the pair pre-filter (strict fp64 / fp32 modes; <= 32768 spheres, with a third
+                                level of boxes -- one per 512 slots -- and the tables in global memory above 2048) */
 
 /* divergence layout of the trace kernel. Results are identical for all of them. */
 #define TRAY_LAYOUT_AUTO 0
@@ -190,8 +191,8 @@ TRAY_API int64_t tray_query(tray_ctx *ctx, int32_t key);
 
 /* Device-free (host code only, no CUDA call): the two-level cluster tables tray_scene_upload stages for TRAY_ACCEL_CLUSTER,
  * for tests and inspection. Layout of the blob (float4 units): pair pre-filter table in slot order (8 float4 per chunk of 8
- * slots) | chunk boxes from meta[1] (three float4 per pair of chunks: centre, half extent) | group boxes from meta[2] | uint16
- * sphere id per slot from meta[3]. meta = {blob float4s, off_box2, off_box1, off_ids, real groups (multiple of 8), always-groups,
+ * slots) | chunk boxes from meta[1] (three float4 per pair of chunks: centre, half extent) | group boxes from meta[2] | word boxes
+ * (one per 8 groups, padded to a multiple of 8 words) right after them | uint16 sphere id per slot from meta[3]. meta = {blob float4s, off_box2, off_box1, off_ids, real groups (multiple of 8), always-groups,
  * chunk mask of the last always-group, spheres the filter cannot bound}; r_out = max |coordinate| the error bounds assume.
  * Copies at most cap_floats floats; blob_out may be NULL (size query). Scene.Hit reference: ray/objects.go:37-46. */
 TRAY_API int tray_cluster_tables(const tray_scene_desc *scene, float *blob_out, size_t cap_floats, int32_t *meta, float *r_out);
