@@ -18,6 +18,15 @@ def render(layout, accel, w=160, h=90, spp=8, depth=50):
     t.MaxDepth, t.NumRaysPerPixel, t.Seed, t.Layout, t.Accel = depth, spp, 2, layout, accel
     img = t.Render(scene)
     return hashlib.sha1(img.tobytes() + ctx.read_hdr(w, h).tobytes()).hexdigest()[:12], t.Stats["bounds_violations"]
+big = ray.RichScene(rand.New(2), 50)  # 10 001 spheres: the three-level walk
+def render_big():
+    t = ray.New(96, 54); t.Camera = ray.RichSceneCamera()
+    t.MaxDepth, t.NumRaysPerPixel, t.Seed = 12, 4, 2
+    img = t.Render(big)
+    return hashlib.sha1(img.tobytes() + ctx.read_hdr(96, 54).tobytes()).hexdigest()[:12], t.Stats["bounds_violations"], t.Stats["box_tests"]
+hb = {render_big() for _ in range(10)}
+print("10 001 spheres, three-level walk (tables in global memory): 10 runs -> %d distinct image+HDR hashes, refused accesses = %d" % (len({x[0] for x in hb}), sum(int(x[1]) for x in hb)))
+assert len(hb) == 1 and all(x[1] == 0 and x[2] > 0 for x in hb)
 h0, v = render(ray.LAYOUT_PLAIN, ray.ACCEL_AUTO)
 print("bounds-check build over tools/sanitize_run.py + a 160x90x8 render: refused accesses =", int(v))
 assert v == 0

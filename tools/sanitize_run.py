@@ -44,6 +44,22 @@ for n in list(range(0, 21)) + [63, 64, 65, 127, 129, 511, 513]:
         t.MaxDepth, t.NumRaysPerPixel, t.Seed, t.Accel = 6, 2, 5, accel
         out[accel] = t.Render(sc).copy()
     assert np.array_equal(out[ray.ACCEL_CLUSTER], out[ray.ACCEL_BRUTE]), n
+# scenes above 2048 spheres: the three-level walk with its tables in global memory (cluster_scan_big), word counts 5, 6 and 9 (one and two
+# octets of word boxes, partial last word), with an always-group
+for n in (2049, 2600, 4103):
+    objs = [ray.Sphere((float(rs.uniform(-30, 30)), float(rs.uniform(0, 2)), float(rs.uniform(-60, 0))), float(rs.uniform(0.1, 0.5)),
+                       (ray.Lambertian((.5, .6, .7)), ray.Metal((.8, .8, .8), 0.2), ray.Dielectric(1.5))[i % 3]) for i in range(n)]
+    objs.append(ray.Sphere((0, -1000.5, -8), 1000, ray.Lambertian((.5, .5, .5))))
+    sc = ray.Scene(objs, ray.DefaultBackground())
+    out = {}
+    for accel in (ray.ACCEL_AUTO, ray.ACCEL_CLUSTER, ray.ACCEL_BVH, ray.ACCEL_BRUTE):
+        t = ray.New(40, 22)
+        t.Camera = ray.Camera(Position=(0, 3, 6), LookAt=(0, 0, -20), VerticalFoV=50.0)
+        t.MaxDepth, t.NumRaysPerPixel, t.Seed, t.Accel = 6, 2, 5, accel
+        out[accel] = t.Render(sc).copy()
+        if accel in (ray.ACCEL_AUTO, ray.ACCEL_CLUSTER):
+            assert t.Stats["box_tests"] > 0, n
+    assert all(np.array_equal(v, out[ray.ACCEL_BRUTE]) for v in out.values()), n
 # device LBVH build + traversal on a scene large enough for it
 big = ray.RichScene(rand.New(2), 20)
 ctx.configure(_lib.CFG_BVH_BUILD, _lib.BVH_BUILD_DEVICE)
