@@ -359,6 +359,22 @@ def test_dense_scene_10k_spheres(ctx, O):
             assert t.Stats["box_tests"] > 0  # the cluster walk ran (cluster_scan_big), not the per-lane BVH
 
 
+def test_cluster_walk_at_its_size_limit(ctx):
+    """32 401 spheres = 64 words: the whole 64-bit word mask of the three-level walk is in use; one grid row more and the scene
+    falls back to the per-lane BVH. Same bits either way."""
+    outs = {}
+    for half, accel in ((90, ray.ACCEL_AUTO), (90, ray.ACCEL_BVH), (91, ray.ACCEL_AUTO), (91, ray.ACCEL_BVH)):
+        scene = ray.RichScene(rand.New(2), half=half)
+        t = tracer(64, 36, 2, 8)
+        t.Accel = accel
+        outs[half, accel] = (t.Render(scene).copy(), t.Stats["segments"], t.Stats["box_tests"])
+    assert 32000 < len(ray.RichScene(rand.New(2), half=90).Objects) <= 32768 < len(ray.RichScene(rand.New(2), half=91).Objects)
+    for half in (90, 91):
+        a, b = outs[half, ray.ACCEL_AUTO], outs[half, ray.ACCEL_BVH]
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], half
+    assert outs[90, ray.ACCEL_AUTO][2] > 0 and outs[91, ray.ACCEL_AUTO][2] == 0 and outs[90, ray.ACCEL_BVH][2] == 0
+
+
 # ---- full-size properties (BASELINE config 2: 1920x1080, 64 rays/pixel, depth 50) ---------------------------
 def test_full_size_properties(ctx, O):
     w, h, spp, depth = 1920, 1080, 64, 50
