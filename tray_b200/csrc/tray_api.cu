@@ -425,8 +425,8 @@ int launch_trace_wavefront(Device& d, const TraceArgs& A, const DevScene<double>
 #ifndef TRAY_DEFAULT_LAYOUT
 #define TRAY_DEFAULT_LAYOUT TRAY_LAYOUT_PLAIN  // config 2, with the camera rays generated ahead: plain 99.7 ms, regroup 101.8, wavefront 120.9
 #endif
-// AUTO: two-level clusters while the scene is small enough for their tables (and the filter can bound nearly all of it),
-// the per-lane BVH above; BRUTE: the linear scan in the reference's Scene.Hit order.
+// AUTO: the cluster walk while the scene is small enough for its tables (32768 spheres) and the filter can bound nearly all of
+// it, the per-lane BVH otherwise; BRUTE: the linear scan in the reference's Scene.Hit order.
 constexpr int kAutoClusterMax = 32768, kAutoClusterUnfilterable = 64;
 int closest_hit_structure(const tray_ctx* ctx, const Device& d, int accel) {
     const bool cluster_ok = d.cl_present;
@@ -588,9 +588,10 @@ bool bvh_build_device(Device& d, const tray_scene_desc* sc, const std::vector<in
 }
 
 // ---- two-level cluster tables for cluster_scan (tray_kernels.cuh) ------------------------------------------------
-// Spheres the pre-filter can bound are split recursively at the median of the longest centroid axis into groups of 64
-// and those into chunks of 8 (every part full except the last), so that chunk = 8 consecutive slots and group = 8
-// consecutive chunks are spatially compact. Spheres outside the filter's range (|C|inf > 256, r^2 > 256, non-finite) and,
+// Spheres the pre-filter can bound are split recursively at the median of the longest centroid axis into words of 512, those
+// into groups of 64 and those into chunks of 8 (every part full except the last; a word is padded to 8 group slots, a group to
+// 8 chunk slots), so that chunk = 8 consecutive slots, group = 8 consecutive chunks and word = 8 consecutive groups are
+// spatially compact; every level gets its conservative fp32 box. Spheres outside the filter's range (|C|inf > 256, r^2 > 256, non-finite) and,
 // when there are only a few, spheres much larger than the rest go into "always" groups that every ray scans.
 struct ClusterHost {
     std::vector<float4> blob;
@@ -897,7 +898,8 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             fp[2 * j] = make_float4(c[0][0], c[1][0], c[0][1], c[1][1]);
             fp[2 * j + 1] = make_float4(c[0][2], c[1][2], nk[0], nk[1]);
         }
-        // two-level cluster tables (the default closest-hit structure up to kClusterMaxSpheres spheres)
+        // cluster tables (the default closest-hit structure up to kClusterMaxSpheres spheres: staged into shared memory and walked
+        // on two levels up to kSmemClusterMax spheres, read from global memory and walked on three levels above)
         ClusterHost clh;
         const bool use_clusters = n <= kClusterMaxSpheres;
         if (use_clusters) clh = build_clusters(sc, n);
