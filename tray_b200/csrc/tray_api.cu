@@ -920,23 +920,23 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
             d.bvh_n_always = (int)hb.always.size(); d.bvh_extent = hb.extent;
             if (!hb.always.empty()) {
                 grow(d.bvh_always, d.cap_always, hb.always.size());
-                CK(cudaMemcpy(d.bvh_always, hb.always.data(), sizeof(int) * hb.always.size(), cudaMemcpyHostToDevice));
+                CK(cudaMemcpyAsync(d.bvh_always, hb.always.data(), sizeof(int) * hb.always.size(), cudaMemcpyHostToDevice, d.stream));
             }
             grow(d.fpair, d.cap_fpair, (size_t)n_pad);
-            CK(cudaMemcpy(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(d.fpair, fp.data(), sizeof(float4) * n_pad, cudaMemcpyHostToDevice, d.stream));
             grow(d.geo_d, d.cap_geo_d, (size_t)n_alloc); grow(d.geo_f, d.cap_geo_f, (size_t)n_alloc);
             grow(d.radius_d, d.cap_radius_d, (size_t)n_alloc); grow(d.radius_f, d.cap_radius_f, (size_t)n_alloc);
             grow(d.kind, d.cap_kind, (size_t)n_alloc); grow(d.params, d.cap_params, (size_t)n_alloc);
-            CK(cudaMemcpy(d.geo_d, gd.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.geo_f, gf.data(), sizeof(float4) * n_alloc, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.radius_d, rd.data(), sizeof(double) * n_alloc, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.radius_f, rf.data(), sizeof(float) * n_alloc, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.kind, kd.data(), n_alloc, cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d.params, pr.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(d.geo_d, gd.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.geo_f, gf.data(), sizeof(float4) * n_alloc, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.radius_d, rd.data(), sizeof(double) * n_alloc, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.radius_f, rf.data(), sizeof(float) * n_alloc, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.kind, kd.data(), n_alloc, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.params, pr.data(), sizeof(double4) * n_alloc, cudaMemcpyHostToDevice, d.stream));
             d.cl_present = false;
             if (use_clusters) {
                 grow(d.cl_blob, d.cap_cl_blob, clh.blob.size());
-                CK(cudaMemcpy(d.cl_blob, clh.blob.data(), sizeof(float4) * clh.blob.size(), cudaMemcpyHostToDevice));
+                CK(cudaMemcpyAsync(d.cl_blob, clh.blob.data(), sizeof(float4) * clh.blob.size(), cudaMemcpyHostToDevice, d.stream));
                 d.cl_blob_f4 = (int)clh.blob.size(); d.cl_off_box2 = clh.off_box2; d.cl_off_box1 = clh.off_box1; d.cl_off_box0 = clh.off_box0; d.cl_off_ids = clh.off_ids;
                 d.cl_real_groups = clh.real_groups; d.cl_always_groups = clh.always_groups; d.cl_always_last = clh.always_last; d.cl_r = clh.r;
                 d.cl_present = true;
@@ -948,12 +948,15 @@ int tray_scene_upload(tray_ctx* ctx, const tray_scene_desc* sc) {
                 if (!host_built) { std::vector<int> tmp = tree_ids; bvh_build_host(sc, hb, tmp); host_built = true; }
                 if (!hb.nodes.empty()) {
                     grow(d.bvh, d.cap_bvh, hb.nodes.size());
-                    CK(cudaMemcpy(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpyAsync(d.bvh, hb.nodes.data(), sizeof(BvhNode) * hb.nodes.size(), cudaMemcpyHostToDevice, d.stream));
                     grow(d.bvh_leaf_ids, d.cap_leaf, hb.leaf_ids.size());
                     d.bvh_present = true;
-                    CK(cudaMemcpy(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpyAsync(d.bvh_leaf_ids, hb.leaf_ids.data(), sizeof(int) * hb.leaf_ids.size(), cudaMemcpyHostToDevice, d.stream));
                 }
             }
+            // the tables travel as asynchronous copies on the device's stream (the pageable sources above are staged by the driver when the
+            // call is made); one wait per device instead of one per table
+            CK(cudaStreamSynchronize(d.stream));
         }
         for (int i = 0; i < 3; i++) { ctx->bg_a[i] = sc->bg_a[i]; ctx->bg_b[i] = sc->bg_b[i]; }
         ctx->host_geo_d = gd; ctx->host_geo_f = gf;
