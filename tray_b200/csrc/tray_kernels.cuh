@@ -20,6 +20,7 @@ constexpr int kMaxDepth = 256;   // attenuation-stack capacity (ids); tray_rende
 #endif
 constexpr int kCand = TRAY_CH + 8;  // deferred candidates per lane before an in-loop flush
 constexpr int kBatch = 128;      // samples a warp takes from the global counter at a time
+constexpr int kBatchSmall = 32;  // ... in the instantiation for passes with few samples per warp (config 1: 380): the warps run dry together
 constexpr unsigned kFull = 0xffffffffu;
 
 // Bounds-check build (-DTRAY_BOUNDS_CHECK, tools/gpu_bounds.sh): every table / list / stack / scratch access of the trace
@@ -824,7 +825,7 @@ struct RegroupBuf {
 #else
 #define TRAY_TRACE_BOUNDS(TPB, MINB) __launch_bounds__(TPB, MINB)
 #endif
-template <typename T, bool FMA, int TPB, int MINB, int GEO, bool REGROUP = false>
+template <typename T, bool FMA, int TPB, int MINB, int GEO, bool REGROUP = false, int BATCH = kBatch>
 __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant__ TraceArgs A, const __grid_constant__ DevScene<T> S,
                                                           const __grid_constant__ GeoArg<T, GEO> GP) {
     typedef typename Vec4T<T>::type T4;
@@ -880,11 +881,11 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 if (pool_next >= pool_end) {
 #endif
                     unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)kBatch);
+                    if (lane == 0) base = atomicAdd(A.counter, (unsigned long long)BATCH);
                     base = __shfl_sync(kFull, base, 0);
                     if (base >= A.n_samples) { exhausted = true; break; }
                     pool_next = (unsigned)base;
-                    pool_end = (unsigned)base + kBatch < n_samples ? (unsigned)base + kBatch : n_samples;
+                    pool_end = (unsigned)base + BATCH < n_samples ? (unsigned)base + BATCH : n_samples;
                 }
 #if TRAY_GEN_INKERNEL
                 if (gen_avail == 0) {  // the whole warp generates the camera rays of the next (up to) kGenSlots samples of its batch
