@@ -671,6 +671,9 @@ def run_ours(args):
                          "issue_active": prof.get("issue_active") if prof else None,
                          "threads_per_instruction": prof.get("threads_per_instruction") if prof else None,
                          "frac_fp64_brute": frac_fp64_brute,
+                         # SURVEY 8(d)'s other reading ("N_tested = kernel-counted tests for BVH runs"): only the spheres the kernel looked at
+                         "frac_kernel_counted_tests": (algorithmic_flops(segments, n_spheres, sphere_tests) / (trace_ms * 1e-3) / 1e12 / peak_used
+                                                       if peak_used and trace_ms > 0 else None),
                          "ns_per_segment": ({"total_smsp_ns": ns_seg, **{k: ns_seg * v for k, v in prof.get("time_share", {}).items()},
                                              "note": "SM-sub-partition time per ray segment (trace-kernel time x 592 sub-partitions / segments), split by the "
                                                      "stall-sample shares of the committed capture (%s)" % prof.get("source")} if prof else {"total_smsp_ns": ns_seg}),
