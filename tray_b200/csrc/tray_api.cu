@@ -323,7 +323,11 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 #ifndef TRAY_CLUSTER_MINB
 #define TRAY_CLUSTER_MINB 4
 #endif
-    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB : ((GEO == kGeoCluster || GEO == kGeoClusterBig) ? TRAY_CLUSTER_MINB : kMinBlocks);
+#ifndef TRAY_FP32_MINB
+#define TRAY_FP32_MINB 7
+#endif
+    constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB
+                       : ((GEO == kGeoCluster || GEO == kGeoClusterBig) ? (sizeof(T) == 4 ? TRAY_FP32_MINB : TRAY_CLUSTER_MINB) : kMinBlocks);
     auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
     if constexpr (GEO == kGeoCluster && sizeof(T) == 8 && !FMA) {
         // small passes (config 1: 380 samples per resident warp) take the counter in steps of 32 instead of 128 samples: a separate

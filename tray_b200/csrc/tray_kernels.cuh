@@ -71,6 +71,19 @@ struct TraceArgs {
 #ifndef TRAY_GEN_INKERNEL
 #define TRAY_GEN_INKERNEL 1
 #endif
+#ifndef TRAY_FP32_PARK
+#define TRAY_FP32_PARK 0  // fp32 fast path: 1 = park the path state across the scan like the fp64 kernels (in float slots), 0 = keep it in registers
+#endif
+#ifndef TRAY_FP32_SKIP_ORIGIN
+// fp32 fast path: a ray that leaves a sphere to its outside cannot meet that sphere again (convex), but in float32 the ground
+// (r = 1000: c = |C-O|^2 - r^2 cancels to +-0.06) reports such hits beyond FrontEpsilon: 8 % more ray segments and a darker
+// ground. 1 = the exact test skips the sphere of origin for outward rays (geometrically exact; the fp64 modes follow the
+// reference and test everything).
+#define TRAY_FP32_SKIP_ORIGIN 1
+#endif
+#ifndef TRAY_FP32_SCANCONST
+#define TRAY_FP32_SCANCONST 0  // fp32 fast path: the per-ray constants of the scan in float32 (wider margins) instead of through fp64
+#endif
 // TRAY_GEN_INKERNEL (default): every warp generates the camera rays of its next 32 samples itself -- all 32 lanes busy --
 // into a shared-memory pool, and regeneration takes them from there (measured 95.9 ms per config-2 frame). With 0 a separate
 // camera_ray_kernel makes all camera rays of the pass ahead and they travel through HBM, 64 B/path each way (97.8 ms).
@@ -274,7 +287,7 @@ __device__ __forceinline__ void bvh_closest_hit(const DevScene<T>& S, const type
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* sfp, const typename Vec4T<T>::type* __restrict__ ggeo,
                                     uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a,
-                                    T& best_t, int& best, int& ncand, unsigned& mask_prev, const volatile double* parked = nullptr) {
+                                    T& best_t, int& best, int& ncand, unsigned& mask_prev, const volatile T* parked = nullptr) {
     constexpr int CH = TRAY_CH;
     const int n_pad = S.n_pad;
     // ---- fp32 conservative pre-filter (packed FFMA2, two spheres per instruction, 8 instructions per pair) ----
@@ -384,7 +397,7 @@ __device__ __forceinline__ void filter_scan(const DevScene<T>& S, const float4* 
 // the upper bound is strict (fl(x/a) > best_t whenever x >= best_t*a*(1+2^-49)), so a tie with a lower id is never skipped.
 template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::type* __restrict__ ggeo, const uint16_t* cand, int ncand,
-                                                       T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best) {
+                                                       T ox, T oy, T oz, T dx, T dy, T dz, T a, T& best_t, int& best, int skip = -1) {
     const T tmin = front_epsilon<T>();
     const T ra = trcp(a);  // every root is divided by the same a: one reciprocal chain per ray segment (rcp_refined)
     const T up = sizeof(T) == 8 ? T(1.0000000000000018) : T(1.000002), dn = sizeof(T) == 8 ? T(0.9999999999999991) : T(0.999999);
@@ -394,6 +407,7 @@ __device__ __forceinline__ void resolve_candidates_lex(const typename Vec4T<T>::
     for (int k = 0; k < ncand; k++) {  // (not unrolled: one copy of the exact test in the instruction cache)
         const int id = cand[k * TPB];
         if (!TRAY_CHECK(k < kCand && id >= 0 && id <= 65535)) continue;  // (the table holds n_pad + 8 entries; ids come from the staged tables)
+        if constexpr (sizeof(T) == 4 && TRAY_FP32_SKIP_ORIGIN) { if (id == skip) continue; }  // fp32 fast path: the sphere the ray leaves outwards
         typename Vec4T<T>::type g = ggeo[id];
         T h, c, disc, root;
         sphere_terms<T, FMA>(ox, oy, oz, dx, dy, dz, a, g.x, g.y, g.z, g.w, h, c, disc);
@@ -449,24 +463,41 @@ template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4* sblob, const typename Vec4T<T>::type* __restrict__ ggeo,
                                              uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a, T udx, T udy, T udz,
                                              T& best_t, int& best, int& ncand, unsigned& nchunks, unsigned& nboxes,
-                                             const volatile double* parked = nullptr) {
+                                             const volatile T* parked = nullptr) {
     // ---- per-ray constants of the pair pre-filter (as filter_scan; the unit direction is Unit(D) of the RayColor step,
     //      computed by the caller in fp64 with IEEE sqrt and divisions: within 2 ulp of D/|D|, far inside the bounds) ----
     const float u32 = 5.9604645e-8f;
+    float fdx, fdy, fdz, ndo, mo, R, eh, noot;
+    bool off;
+    constexpr bool kF32Const = sizeof(T) == 4 && TRAY_FP32_SCANCONST;
+    if constexpr (kF32Const) {
+        // fp32 fast path (no parity claim): the same constants without the trip through fp64; the extra roundings (a few u R
+        // each) are covered by wider margins, the tests stay conservative with respect to the fp32 exact test up to its own error
+        fdx = (float)udx; fdy = (float)udy; fdz = (float)udz;
+        const float fox = (float)ox, foy = (float)oy, foz = (float)oz;
+        ndo = -((fdx * fox + fdy * foy) + fdz * foz);
+        mo = 1.0000002f * fmaxf(fabsf(fox), fmaxf(fabsf(foy), fabsf(foz)));
+        R = S.cl_r + mo;
+        eh = 24.0f * u32 * R;
+        noot = (1.5f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) - ((fox * fox + foy * foy) + foz * foz);
+        off = !(mo < 1e6f) || !((float)a > 0.0f && (float)a < 3.0e38f);
+    } else {
     const double ddx = (double)udx, ddy = (double)udy, ddz = (double)udz;
-    const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
-    float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
-    const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
-    const float R = S.cl_r + mo;
-    float eh = 17.5f * u32 * R;
-    float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+    fdx = (float)ddx; fdy = (float)ddy; fdz = (float)ddz;
+    ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+    mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+    R = S.cl_r + mo;
+    eh = 17.5f * u32 * R;
+    noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
                          ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));
     // origin too far out, or a direction without a finite positive length: no culling at all for this ray
-    const bool off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
+    off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
+    }
     if (off) { noot = __int_as_float(0x7f800000); eh = 0.0f; }
     ndo += eh;
     const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
-    const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
+    const float px = kF32Const ? 2.0f * (float)ox : (float)(2.0 * (double)ox), py = kF32Const ? 2.0f * (float)oy : (float)(2.0 * (double)oy),
+                pz = kF32Const ? 2.0f * (float)oz : (float)(2.0 * (double)oz);
     const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
     const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
     // ---- per-ray constants of the box test ----
@@ -477,8 +508,9 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
         return r;
     };
     const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
-    const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
-    const float ks = 16.0f * u32 * R;
+    const float nqx = kF32Const ? -((float)ox * ix) : -(float)((double)ox * (double)ix), nqy = kF32Const ? -((float)oy * iy) : -(float)((double)oy * (double)iy),
+                nqz = kF32Const ? -((float)oz * iz) : -(float)((double)oz * (double)iz);
+    const float ks = (kF32Const ? 24.0f : 16.0f) * u32 * R;
     const float2 IX = make_float2(ix, ix), IY = make_float2(iy, iy), IZ = make_float2(iz, iz);
     const float2 NQX = make_float2(nqx, nqx), NQY = make_float2(nqy, nqy), NQZ = make_float2(nqz, nqz);
     const float2 AX = make_float2(fabsf(ix), fabsf(ix)), AY = make_float2(fabsf(iy), fabsf(iy)), AZ = make_float2(fabsf(iz), fabsf(iz));
@@ -631,7 +663,7 @@ template <typename T, bool FMA, int TPB>
 __device__ __forceinline__ void cluster_scan_big(const DevScene<T>& S, const typename Vec4T<T>::type* __restrict__ ggeo,
                                                  uint16_t* cand, bool has, T ox, T oy, T oz, T dx, T dy, T dz, T a, T udx, T udy, T udz,
                                                  T& best_t, int& best, int& ncand, unsigned& nchunks, unsigned& nboxes,
-                                                 const volatile double* parked = nullptr) {
+                                                 const volatile T* parked = nullptr) {
     // ---- per-ray constants: as cluster_scan ----
     const float u32 = 5.9604645e-8f;
     const double ddx = (double)udx, ddy = (double)udy, ddz = (double)udz;
@@ -864,6 +896,8 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
     V3<T> O = mk<T>(T(0), T(1e18), T(0)), D = mk<T>(T(0), T(1), T(0));
     Pcg rng = pcg_new_idx(0, 0);
     int depth_left = 0, sp = 0;
+    int skip = -1;  // fp32 fast path (TRAY_FP32_SKIP_ORIGIN): sphere the current ray leaves outwards, -1 = none
+    (void)skip;
     uint16_t stk[REGROUP ? 1 : kMaxDepth];
     unsigned slot = blockIdx.x * TPB + tid;  // regroup layout: where this path's attenuation stack lives
     unsigned long long nseg = 0, ntests = 0, nbox = 0;
@@ -923,6 +957,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     D = mk<T>(T(d64.x), T(d64.y), T(d64.z));
                     depth_left = A.max_depth;
                     sp = 0;
+                    skip = -1;
                     has = true;
                 }
                 unsigned cnt = __popc(need);
@@ -952,7 +987,19 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         __shared__ int s_parki[3][TPB];
         volatile double* pk = &s_park[0][tid];
         volatile int* pki = &s_parki[0][tid];
-        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP;
+        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP && sizeof(T) == 8;
+        // fp32 fast path: the same parking in float slots (52 instead of 100 bytes per thread: a sixth CTA fits the SM's shared memory)
+        constexpr bool kParkF = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP && sizeof(T) == 4 && TRAY_FP32_PARK;
+        __shared__ float s_parkf[14][TPB];
+        volatile float* pkf = &s_parkf[0][tid];
+        if constexpr (kParkF) {
+            pkf[0] = (float)O.x; pkf[TPB] = (float)O.y; pkf[2 * TPB] = (float)O.z;
+            pkf[3 * TPB] = (float)D.x; pkf[4 * TPB] = (float)D.y; pkf[5 * TPB] = (float)D.z;
+            pkf[6 * TPB] = __uint_as_float((unsigned)rng.hi); pkf[7 * TPB] = __uint_as_float((unsigned)(rng.hi >> 32));
+            pkf[8 * TPB] = __uint_as_float((unsigned)rng.lo); pkf[9 * TPB] = __uint_as_float((unsigned)(rng.lo >> 32));
+            pki[0] = depth_left; pki[TPB] = sp; pki[2 * TPB] = (int)my_li;
+            if constexpr (TRAY_FP32_SKIP_ORIGIN) pkf[13 * TPB] = __int_as_float(skip);
+        }
         if constexpr (kPark) {
             pk[0] = (double)O.x; pk[TPB] = (double)O.y; pk[2 * TPB] = (double)O.z;
             pk[3 * TPB] = (double)D.x; pk[4 * TPB] = (double)D.y; pk[5 * TPB] = (double)D.z;
@@ -965,6 +1012,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         { const T l = tsqrt_hot(len2(D)); ud = div3_hot(D, l); }  // Unit(r.Direction), ray/vec3.go
 #if TRAY_PARK_STATE
         if constexpr (kPark) { pk[8 * TPB] = (double)ud.x; pk[9 * TPB] = (double)ud.y; pk[10 * TPB] = (double)ud.z; }
+        if constexpr (kParkF) { pkf[10 * TPB] = (float)ud.x; pkf[11 * TPB] = (float)ud.y; pkf[12 * TPB] = (float)ud.z; }
 #endif
         T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
         T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
@@ -988,6 +1036,20 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 rng.hi = (uint64_t)__double_as_longlong(pk[6 * TPB]); rng.lo = (uint64_t)__double_as_longlong(pk[7 * TPB]);
                 depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
                 ud = mk<T>(T(pk[8 * TPB]), T(pk[9 * TPB]), T(pk[10 * TPB]));
+            } else if constexpr (kParkF) {
+                const volatile T* pkt = reinterpret_cast<const volatile T*>(pkf);
+                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pkt);
+                else if constexpr (GEO == kGeoClusterBig) cluster_scan_big<T, FMA, TPB>(S, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pkt);
+                else
+                filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pkt);
+                ox = T(pkf[0]); oy = T(pkf[TPB]); oz = T(pkf[2 * TPB]); dx = T(pkf[3 * TPB]); dy = T(pkf[4 * TPB]); dz = T(pkf[5 * TPB]);
+                a = (dx * dx + dy * dy) + dz * dz;
+                O = mk<T>(ox, oy, oz); D = mk<T>(dx, dy, dz);
+                rng.hi = (uint64_t)__float_as_uint(pkf[6 * TPB]) | ((uint64_t)__float_as_uint(pkf[7 * TPB]) << 32);
+                rng.lo = (uint64_t)__float_as_uint(pkf[8 * TPB]) | ((uint64_t)__float_as_uint(pkf[9 * TPB]) << 32);
+                depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
+                ud = mk<T>(T(pkf[10 * TPB]), T(pkf[11 * TPB]), T(pkf[12 * TPB]));
+                if constexpr (TRAY_FP32_SKIP_ORIGIN) skip = __float_as_int(pkf[13 * TPB]);
             } else
 #endif
             {
@@ -1023,7 +1085,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         }
         }
         if constexpr (GEO == kGeoCluster || GEO == kGeoClusterBig) {
-            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best);
+            resolve_candidates_lex<T, FMA, TPB>(ggeo, cand, ncand, ox, oy, oz, dx, dy, dz, a, best_t, best, skip);
         } else {
             if (mask_prev)
                 push_candidates<T, FMA, TPB, CH>(ggeo, cand, &ncand, mask_prev, n_pad - CH, ox, oy, oz, dx, dy, dz, a, &best_t, &best);
@@ -1095,7 +1157,10 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 // one shared UnitVector draw site for Lambertian (always) and Metal (iff Fuzz > 0)
                 const bool need_uv = kind == 0 || (kind == 1 && prm.w > 0.0);
                 V3<T> uv = mk<T>(T(0), T(0), T(0));
-                if (need_uv) { V3<double> u64 = pcg_unit_vector(rng, zig, S.unitvec_variant); uv = mk<T>(T(u64.x), T(u64.y), T(u64.z)); }
+                if (need_uv) {
+                    if constexpr (sizeof(T) == 4 && TRAY_FP32_RNG) uv = pcg_unit_vector_f32(rng, zig, S.unitvec_variant);  // fp32 fast path: float normals
+                    else { V3<double> u64 = pcg_unit_vector(rng, zig, S.unitvec_variant); uv = mk<T>(T(u64.x), T(u64.y), T(u64.z)); }
+                }
                 bool scattered = true;
                 V3<T> D2;
                 if (kind == 0) {  // Lambertian.Scatter, materials.go:13-21
@@ -1122,6 +1187,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                         else if (TRAY_CHECK(sp >= 0 && sp < kMaxDepth && best >= 0 && best < S.n)) stk[sp] = (uint16_t)best;
                         sp++;
                     }
+                    if constexpr (sizeof(T) == 4 && TRAY_FP32_SKIP_ORIGIN && !REGROUP) skip = ((dot(D2, N) > T(0)) == front) ? best : -1;  // (not part of the regroup exchange)
                     O = P; D = D2;
                     depth_left--;
                     if (depth_left <= 0) { finish = true; nexh++; }  // RayColor(depth<=0) = black
