@@ -419,17 +419,24 @@ def test_full_size_properties(ctx, O):
 
 
 def test_fp32_mode_reports_psnr(ctx):
-    """The fp32 path is reported separately with its PSNR against fp64 (no bit-level claim; north_star: "fp32 mode reports
-    PSNR"). BASELINE config 2, where bench.py quotes it: measured 52.4 dB, 92.6 % of the pixels within 1 LSB. It is NOT a
-    fast path any more: with the two-level closest hit the strict fp64 default is as fast."""
+    """The fp32 fast path is reported separately with its PSNR against fp64 (no bit-level claim; north_star: "fp32 mode reports
+    PSNR"). BASELINE config 2, where bench.py quotes it: measured 61.4 dB, 99.6 % of the pixels within 1 LSB, 1.35x the speed
+    of the strict fp64 default. It traces the same paths: a ray leaving a sphere outwards never re-tests that sphere (in
+    float32 the r = 1000 ground reported false hits beyond FrontEpsilon: 8 % more segments, 52 dB), so the number of ray
+    segments per path stays within 0.5 % of the fp64 figure."""
     scene = ray.RichScene(rand.New(2))
-    a = tracer(1920, 1080, 64, 50).Render(scene).astype(np.float64)
-    b = tracer(1920, 1080, 64, 50, precision=ray.FP32).Render(scene).astype(np.float64)
+    ta = tracer(1920, 1080, 64, 50)
+    a = ta.Render(scene).astype(np.float64)
+    seg64 = ta.Stats["segments"] / ta.Stats["paths"]
+    tb = tracer(1920, 1080, 64, 50, precision=ray.FP32)
+    b = tb.Render(scene).astype(np.float64)
+    seg32 = tb.Stats["segments"] / tb.Stats["paths"]
     mse = ((a[:, :, :3] - b[:, :, :3]) ** 2).mean()
     psnr = 10 * np.log10(255.0 ** 2 / mse)
     within = (np.abs(a[:, :, :3] - b[:, :, :3]).max(axis=2) <= 1).mean()
-    print("fp32 PSNR vs fp64: %.2f dB, %.4f of the pixels within 1 LSB" % (psnr, within))
-    assert psnr > 50.0 and within > 0.9
+    print("fp32 PSNR vs fp64: %.2f dB, %.4f of the pixels within 1 LSB, segments per path %.4f vs %.4f" % (psnr, within, seg32, seg64))
+    assert psnr > 58.0 and within > 0.99
+    assert abs(seg32 / seg64 - 1.0) < 0.005
 
 
 # ---- "next" row 8(f)-1: on-device BiLinear downscale + half-block ANSI frame (BASELINE config 5) ---------------

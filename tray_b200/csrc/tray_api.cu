@@ -324,7 +324,7 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
 #define TRAY_CLUSTER_MINB 4
 #endif
 #ifndef TRAY_FP32_MINB
-#define TRAY_FP32_MINB 7
+#define TRAY_FP32_MINB 6
 #endif
     constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB
                        : ((GEO == kGeoCluster || GEO == kGeoClusterBig) ? (sizeof(T) == 4 ? TRAY_FP32_MINB : TRAY_CLUSTER_MINB) : kMinBlocks);

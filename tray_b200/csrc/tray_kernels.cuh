@@ -71,15 +71,21 @@ struct TraceArgs {
 #ifndef TRAY_GEN_INKERNEL
 #define TRAY_GEN_INKERNEL 1
 #endif
-#ifndef TRAY_FP32_PARK
-#define TRAY_FP32_PARK 0  // fp32 fast path: 1 = park the path state across the scan like the fp64 kernels (in float slots), 0 = keep it in registers
-#endif
 #ifndef TRAY_FP32_SKIP_ORIGIN
 // fp32 fast path: a ray that leaves a sphere to its outside cannot meet that sphere again (convex), but in float32 the ground
 // (r = 1000: c = |C-O|^2 - r^2 cancels to +-0.06) reports such hits beyond FrontEpsilon: 8 % more ray segments and a darker
 // ground. 1 = the exact test skips the sphere of origin for outward rays (geometrically exact; the fp64 modes follow the
 // reference and test everything).
 #define TRAY_FP32_SKIP_ORIGIN 1
+#endif
+#ifndef TRAY_UNWIND_PREFETCH
+#define TRAY_UNWIND_PREFETCH 0
+#endif
+#ifndef TRAY_FP32_FORWARD
+// fp32 fast path: the attenuation product is carried forward along the path ((a1*a2)*a3 ... * sky) instead of the reference's
+// product on unwind (a1*(a2*(a3*sky)), objects.go:56): the same product up to float32 rounding, no id stack and no unwind loop
+// (two dependent loads per level for the 4-5 lanes that finish in an iteration: 6 % of the fp32 kernel's stall samples).
+#define TRAY_FP32_FORWARD 1
 #endif
 #ifndef TRAY_FP32_SCANCONST
 #define TRAY_FP32_SCANCONST 0  // fp32 fast path: the per-ray constants of the scan in float32 (wider margins) instead of through fp64
@@ -898,7 +904,10 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
     int depth_left = 0, sp = 0;
     int skip = -1;  // fp32 fast path (TRAY_FP32_SKIP_ORIGIN): sphere the current ray leaves outwards, -1 = none
     (void)skip;
-    uint16_t stk[REGROUP ? 1 : kMaxDepth];
+    constexpr bool kForward = sizeof(T) == 4 && TRAY_FP32_FORWARD && !REGROUP;  // fp32 fast path: throughput carried forward, no id stack
+    V3<T> thr = mk<T>(T(1), T(1), T(1));
+    (void)thr;
+    uint16_t stk[(REGROUP || kForward) ? 1 : kMaxDepth];
     unsigned slot = blockIdx.x * TPB + tid;  // regroup layout: where this path's attenuation stack lives
     unsigned long long nseg = 0, ntests = 0, nbox = 0;
     unsigned nexh = 0, ndone = 0, ntests_blk = 0, nbox_blk = 0;
@@ -958,6 +967,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     depth_left = A.max_depth;
                     sp = 0;
                     skip = -1;
+                    if constexpr (kForward) thr = mk<T>(T(1), T(1), T(1));
                     has = true;
                 }
                 unsigned cnt = __popc(need);
@@ -987,19 +997,7 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         __shared__ int s_parki[3][TPB];
         volatile double* pk = &s_park[0][tid];
         volatile int* pki = &s_parki[0][tid];
-        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP && sizeof(T) == 8;
-        // fp32 fast path: the same parking in float slots (52 instead of 100 bytes per thread: a sixth CTA fits the SM's shared memory)
-        constexpr bool kParkF = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP && sizeof(T) == 4 && TRAY_FP32_PARK;
-        __shared__ float s_parkf[14][TPB];
-        volatile float* pkf = &s_parkf[0][tid];
-        if constexpr (kParkF) {
-            pkf[0] = (float)O.x; pkf[TPB] = (float)O.y; pkf[2 * TPB] = (float)O.z;
-            pkf[3 * TPB] = (float)D.x; pkf[4 * TPB] = (float)D.y; pkf[5 * TPB] = (float)D.z;
-            pkf[6 * TPB] = __uint_as_float((unsigned)rng.hi); pkf[7 * TPB] = __uint_as_float((unsigned)(rng.hi >> 32));
-            pkf[8 * TPB] = __uint_as_float((unsigned)rng.lo); pkf[9 * TPB] = __uint_as_float((unsigned)(rng.lo >> 32));
-            pki[0] = depth_left; pki[TPB] = sp; pki[2 * TPB] = (int)my_li;
-            if constexpr (TRAY_FP32_SKIP_ORIGIN) pkf[13 * TPB] = __int_as_float(skip);
-        }
+        constexpr bool kPark = (GEO == kGeoFilter || GEO == kGeoCluster || GEO == kGeoClusterBig) && !REGROUP && sizeof(T) == 8;  // (fp32 fast path: state stays in registers -- 72 registers x 28 warps measured best, 33.6 vs 36.2 ms parked)
         if constexpr (kPark) {
             pk[0] = (double)O.x; pk[TPB] = (double)O.y; pk[2 * TPB] = (double)O.z;
             pk[3 * TPB] = (double)D.x; pk[4 * TPB] = (double)D.y; pk[5 * TPB] = (double)D.z;
@@ -1012,7 +1010,6 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
         { const T l = tsqrt_hot(len2(D)); ud = div3_hot(D, l); }  // Unit(r.Direction), ray/vec3.go
 #if TRAY_PARK_STATE
         if constexpr (kPark) { pk[8 * TPB] = (double)ud.x; pk[9 * TPB] = (double)ud.y; pk[10 * TPB] = (double)ud.z; }
-        if constexpr (kParkF) { pkf[10 * TPB] = (float)ud.x; pkf[11 * TPB] = (float)ud.y; pkf[12 * TPB] = (float)ud.z; }
 #endif
         T ox = O.x, oy = O.y, oz = O.z, dx = D.x, dy = D.y, dz = D.z;
         T a = len2(D);  // LengthSquared(r.Direction), objects.go:83 (same bits for every sphere)
@@ -1036,20 +1033,6 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 rng.hi = (uint64_t)__double_as_longlong(pk[6 * TPB]); rng.lo = (uint64_t)__double_as_longlong(pk[7 * TPB]);
                 depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
                 ud = mk<T>(T(pk[8 * TPB]), T(pk[9 * TPB]), T(pk[10 * TPB]));
-            } else if constexpr (kParkF) {
-                const volatile T* pkt = reinterpret_cast<const volatile T*>(pkf);
-                if constexpr (GEO == kGeoCluster) cluster_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pkt);
-                else if constexpr (GEO == kGeoClusterBig) cluster_scan_big<T, FMA, TPB>(S, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, ud.x, ud.y, ud.z, best_t, best, ncand, nchunks, nboxes, pkt);
-                else
-                filter_scan<T, FMA, TPB>(S, sfp, ggeo, cand, has, ox, oy, oz, dx, dy, dz, a, best_t, best, ncand, mask_prev, pkt);
-                ox = T(pkf[0]); oy = T(pkf[TPB]); oz = T(pkf[2 * TPB]); dx = T(pkf[3 * TPB]); dy = T(pkf[4 * TPB]); dz = T(pkf[5 * TPB]);
-                a = (dx * dx + dy * dy) + dz * dz;
-                O = mk<T>(ox, oy, oz); D = mk<T>(dx, dy, dz);
-                rng.hi = (uint64_t)__float_as_uint(pkf[6 * TPB]) | ((uint64_t)__float_as_uint(pkf[7 * TPB]) << 32);
-                rng.lo = (uint64_t)__float_as_uint(pkf[8 * TPB]) | ((uint64_t)__float_as_uint(pkf[9 * TPB]) << 32);
-                depth_left = pki[0]; sp = pki[TPB]; my_li = (unsigned)pki[2 * TPB];
-                ud = mk<T>(T(pkf[10 * TPB]), T(pkf[11 * TPB]), T(pkf[12 * TPB]));
-                if constexpr (TRAY_FP32_SKIP_ORIGIN) skip = __float_as_int(pkf[13 * TPB]);
             } else
 #endif
             {
@@ -1183,7 +1166,8 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                     finish = true;  // absorbed: black
                 } else {
                     if (kind != 2) {  // attenuation = albedo; Dielectric's (1,1,1) is an exact identity
-                        if constexpr (REGROUP) A.stk_g[(size_t)sp * A.n_slots + slot] = (uint16_t)best;
+                        if constexpr (kForward) thr = vmul(thr, mk<T>(T(prm.x), T(prm.y), T(prm.z)));
+                        else if constexpr (REGROUP) A.stk_g[(size_t)sp * A.n_slots + slot] = (uint16_t)best;
                         else if (TRAY_CHECK(sp >= 0 && sp < kMaxDepth && best >= 0 && best < S.n)) stk[sp] = (uint16_t)best;
                         sp++;
                     }
@@ -1194,7 +1178,20 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
                 }
             }
             if (finish) {
-                if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
+                if constexpr (kForward) col = vmul(thr, col);
+                else if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
+#if TRAY_UNWIND_PREFETCH
+                    if constexpr (!REGROUP) {
+                        int id = sp > 0 ? stk[sp - 1] : 0;
+#pragma unroll 1
+                        for (int k = sp - 1; k >= 0; k--) {  // the id of the next level is read while this level's albedo is on its way
+                            const int idn = stk[k > 0 ? k - 1 : 0];
+                            double4 prm = S.params[id];
+                            col = vmul(mk<T>(T(prm.x), T(prm.y), T(prm.z)), col);
+                            id = idn;
+                        }
+                    } else
+#endif
 #pragma unroll 1
                     for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56 (one copy: instruction-cache footprint)
                         int id;
