@@ -439,6 +439,27 @@ def test_fp32_mode_reports_psnr(ctx):
     assert abs(seg32 / seg64 - 1.0) < 0.005
 
 
+def test_fp32_fast_path_other_kernels(ctx):
+    """The fp32 fast path on its other instantiations: the three-level walk of a 10 k-sphere scene (tables in global memory),
+    the linear scan and the regroup layout (which keeps the id stack: the forward product and the origin skip are not part
+    of its exchange). Same streams as fp64, so even at 8 rays per pixel the images agree closely; every pixel gets alpha 255."""
+    for half, accel, layout, w, h in ((50, ray.ACCEL_AUTO, ray.LAYOUT_AUTO, 320, 180), (11, ray.ACCEL_BRUTE, ray.LAYOUT_AUTO, 160, 90),
+                                      (11, ray.ACCEL_AUTO, ray.LAYOUT_REGROUP, 320, 180)):
+        scene = ray.RichScene(rand.New(2), half=half)
+        imgs = {}
+        for prec in (ray.FP64_STRICT, ray.FP32):
+            t = tracer(w, h, 8, 12, precision=prec)
+            t.Accel, t.Layout = accel, layout
+            imgs[prec] = t.Render(scene).astype(np.float64)
+            assert t.Stats["paths"] == w * h * 8
+        a, b = imgs[ray.FP64_STRICT], imgs[ray.FP32]
+        assert (b[:, :, 3] == 255).all()
+        mse = ((a[:, :, :3] - b[:, :, :3]) ** 2).mean()
+        psnr = 10 * np.log10(255.0 ** 2 / mse) if mse > 0 else 99.0
+        print("fp32 vs fp64, %d spheres, accel %d, layout %d: %.1f dB" % (len(scene.Objects), accel, layout, psnr))
+        assert psnr > 35.0, (half, accel, layout, psnr)
+
+
 # ---- "next" row 8(f)-1: on-device BiLinear downscale + half-block ANSI frame (BASELINE config 5) ---------------
 @pytest.mark.parametrize("w,h,cols,rows2", [(640, 360, 160, 90), (320, 200, 79, 50), (257, 131, 64, 32), (64, 36, 64, 36)])
 def test_present_downscale_and_ansi(ctx, O, w, h, cols, rows2):

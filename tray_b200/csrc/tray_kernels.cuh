@@ -78,9 +78,6 @@ struct TraceArgs {
 // reference and test everything).
 #define TRAY_FP32_SKIP_ORIGIN 1
 #endif
-#ifndef TRAY_UNWIND_PREFETCH
-#define TRAY_UNWIND_PREFETCH 0
-#endif
 #ifndef TRAY_FP32_FORWARD
 // fp32 fast path: the attenuation product is carried forward along the path ((a1*a2)*a3 ... * sky) instead of the reference's
 // product on unwind (a1*(a2*(a3*sky)), objects.go:56): the same product up to float32 rounding, no id stack and no unwind loop
@@ -1180,18 +1177,6 @@ __global__ void TRAY_TRACE_BOUNDS(TPB, MINB) trace_kernel(const __grid_constant_
             if (finish) {
                 if constexpr (kForward) col = vmul(thr, col);
                 else if (col.x != T(0) || col.y != T(0) || col.z != T(0)) {
-#if TRAY_UNWIND_PREFETCH
-                    if constexpr (!REGROUP) {
-                        int id = sp > 0 ? stk[sp - 1] : 0;
-#pragma unroll 1
-                        for (int k = sp - 1; k >= 0; k--) {  // the id of the next level is read while this level's albedo is on its way
-                            const int idn = stk[k > 0 ? k - 1 : 0];
-                            double4 prm = S.params[id];
-                            col = vmul(mk<T>(T(prm.x), T(prm.y), T(prm.z)), col);
-                            id = idn;
-                        }
-                    } else
-#endif
 #pragma unroll 1
                     for (int k = sp - 1; k >= 0; k--) {  // Mul(attenuation, ...) applied on unwind, objects.go:56 (one copy: instruction-cache footprint)
                         int id;
