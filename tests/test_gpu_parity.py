@@ -422,8 +422,8 @@ def test_fp32_mode_reports_psnr(ctx):
     """The fp32 fast path is reported separately with its PSNR against fp64 (no bit-level claim; north_star: "fp32 mode reports
     PSNR"). BASELINE config 2, where bench.py quotes it: measured 61.4 dB, 99.6 % of the pixels within 1 LSB, 1.35x the speed
     of the strict fp64 default. It traces the same paths: a ray leaving a sphere outwards never re-tests that sphere (in
-    float32 the r = 1000 ground reported false hits beyond FrontEpsilon: 8 % more segments, 52 dB), so the number of ray
-    segments per path stays within 0.5 % of the fp64 figure."""
+    float32 that test reported a back-face hit for 0.8 % of them and the path then bounced inside the r = 1000 ground until
+    the depth limit: 8 % more segments, 52 dB), so the number of ray segments per path stays within 0.5 % of the fp64 figure."""
     scene = ray.RichScene(rand.New(2))
     ta = tracer(1920, 1080, 64, 50)
     a = ta.Render(scene).astype(np.float64)

@@ -72,10 +72,11 @@ struct TraceArgs {
 #define TRAY_GEN_INKERNEL 1
 #endif
 #ifndef TRAY_FP32_SKIP_ORIGIN
-// fp32 fast path: a ray that leaves a sphere to its outside cannot meet that sphere again (convex), but in float32 the ground
-// (r = 1000: c = |C-O|^2 - r^2 cancels to +-0.06) reports such hits beyond FrontEpsilon: 8 % more ray segments and a darker
-// ground. 1 = the exact test skips the sphere of origin for outward rays (geometrically exact; the fp64 modes follow the
-// reference and test everything).
+// fp32 fast path: a ray that leaves a sphere to its outside cannot meet that sphere again (convex), but in float32 0.8 % of such
+// tests report a hit beyond FrontEpsilon (the r = 1000 ground: c = |C-O|^2 - r^2 cancels to +-0.06; short scattered directions). It
+// is a back-face hit: the normal flips inwards and the path bounces INSIDE the ground until the depth limit -- 8 % more ray
+// segments in all, dark speckles. 1 = the exact test skips the sphere of origin for outward rays (in strict fp64 that test never
+// hits, tests/test_fp32_skip_origin_model.py; the fp64 modes follow the reference and test everything).
 #define TRAY_FP32_SKIP_ORIGIN 1
 #endif
 #ifndef TRAY_FP32_FORWARD
