@@ -104,6 +104,12 @@ func (f *flatScene) walk(objs []Hittable) error {
 				k, p = C.TRAY_MAT_METAL, [4]float64{m.Albedo.x, m.Albedo.y, m.Albedo.z, m.Fuzz}
 			case Dielectric:
 				k, p = C.TRAY_MAT_DIELECTRIC, [4]float64{m.RefIdx, 0, 0, 0}
+			case *Lambertian: // value receivers: pointers satisfy Material as well
+				k, p = C.TRAY_MAT_LAMBERTIAN, [4]float64{m.Albedo.x, m.Albedo.y, m.Albedo.z, 0}
+			case *Metal:
+				k, p = C.TRAY_MAT_METAL, [4]float64{m.Albedo.x, m.Albedo.y, m.Albedo.z, m.Fuzz}
+			case *Dielectric:
+				k, p = C.TRAY_MAT_DIELECTRIC, [4]float64{m.RefIdx, 0, 0, 0}
 			default:
 				return fmt.Errorf("tray cuda: unsupported Material %T (no CPU fallback)", s.Mat)
 			}
@@ -331,10 +337,17 @@ func (t *Tracer) RenderProgressive(scene *Scene, slice int, show func(raysDone i
 			return err
 		}
 		done += k
+		cuda.mu.Lock()
 		ctx := cudaContext()
 		pix := t.imageData.Pix
-		if rc := C.tray_resolve_sums(ctx, C.uint64_t(done), (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.size_t(t.imageData.Stride)); rc != 0 {
-			return fmt.Errorf("tray cuda: %s", C.GoString(C.tray_last_error(ctx)))
+		rc := C.tray_resolve_sums(ctx, C.uint64_t(done), (*C.uint8_t)(unsafe.Pointer(&pix[0])), C.size_t(t.imageData.Stride))
+		var msg string
+		if rc != 0 {
+			msg = C.GoString(C.tray_last_error(ctx))
+		}
+		cuda.mu.Unlock()
+		if rc != 0 {
+			return fmt.Errorf("tray cuda: %s", msg)
 		}
 		if show != nil && !show(done, t.imageData) {
 			return nil
