@@ -41,6 +41,8 @@ var (
 	CUDAReferenceStreams = os.Getenv("TRAY_STREAMS") == "reference"
 	// CUDAFusedFP64 selects the fused-multiply-add discriminant (faster, not bit-identical to Go/amd64).
 	CUDAFusedFP64 = os.Getenv("TRAY_FP64") == "fma"
+	// CUDAFloat32 selects the float32 fast path (1.35x the default on a B200, ~61 dB PSNR against it; no parity claim).
+	CUDAFloat32 = os.Getenv("TRAY_FP32") == "1"
 	// CUDASampleSplit splits samples instead of tiles across devices (partial sums reduced over NVLink).
 	CUDASampleSplit = os.Getenv("TRAY_SPLIT") == "samples"
 )
@@ -201,6 +203,9 @@ func (t *Tracer) renderCUDA(scene *Scene, y0, y1, idx int) error {
 	p.precision = C.TRAY_FP64_STRICT
 	if CUDAFusedFP64 {
 		p.precision = C.TRAY_FP64_FMA
+	}
+	if CUDAFloat32 {
+		p.precision = C.TRAY_FP32
 	}
 	if CUDASampleSplit {
 		p.split_mode = C.TRAY_SPLIT_SAMPLES
