@@ -329,7 +329,7 @@ void launch_trace_geo(const Device& d, const TraceArgs& A, const DevScene<T>& S,
     constexpr int minb = GEO == kGeoFilter ? TRAY_FILTER_MINB
                        : ((GEO == kGeoCluster || GEO == kGeoClusterBig) ? (sizeof(T) == 4 ? TRAY_FP32_MINB : TRAY_CLUSTER_MINB) : kMinBlocks);
     auto k = trace_kernel<T, FMA, kTPB, minb, GEO>;
-    if constexpr (GEO == kGeoCluster && sizeof(T) == 8 && !FMA) {
+    if constexpr (GEO == kGeoCluster && ((sizeof(T) == 8 && !FMA) || sizeof(T) == 4)) {  // (the strict default and the fp32 fast path)
         // small passes (config 1: 380 samples per resident warp) take the counter in steps of 32 instead of 128 samples: a separate
         // instantiation, so that the kernel of the large frames stays byte for byte what it was (0.59 -> 0.49 ms per config-1 frame)
         if (A.n_samples / ((unsigned long long)d.num_sms * 16ull) < 8ull * kBatch) k = trace_kernel<T, FMA, kTPB, minb, GEO, false, kBatchSmall>;
