@@ -85,9 +85,6 @@ struct TraceArgs {
 // (two dependent loads per level for the 4-5 lanes that finish in an iteration: 6 % of the fp32 kernel's stall samples).
 #define TRAY_FP32_FORWARD 1
 #endif
-#ifndef TRAY_FP32_SCANCONST
-#define TRAY_FP32_SCANCONST 0  // fp32 fast path: the per-ray constants of the scan in float32 (wider margins) instead of through fp64
-#endif
 // TRAY_GEN_INKERNEL (default): every warp generates the camera rays of its next 32 samples itself -- all 32 lanes busy --
 // into a shared-memory pool, and regeneration takes them from there (measured 95.9 ms per config-2 frame). With 0 a separate
 // camera_ray_kernel makes all camera rays of the pass ahead and they travel through HBM, 64 B/path each way (97.8 ms).
@@ -471,37 +468,20 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
     // ---- per-ray constants of the pair pre-filter (as filter_scan; the unit direction is Unit(D) of the RayColor step,
     //      computed by the caller in fp64 with IEEE sqrt and divisions: within 2 ulp of D/|D|, far inside the bounds) ----
     const float u32 = 5.9604645e-8f;
-    float fdx, fdy, fdz, ndo, mo, R, eh, noot;
-    bool off;
-    constexpr bool kF32Const = sizeof(T) == 4 && TRAY_FP32_SCANCONST;
-    if constexpr (kF32Const) {
-        // fp32 fast path (no parity claim): the same constants without the trip through fp64; the extra roundings (a few u R
-        // each) are covered by wider margins, the tests stay conservative with respect to the fp32 exact test up to its own error
-        fdx = (float)udx; fdy = (float)udy; fdz = (float)udz;
-        const float fox = (float)ox, foy = (float)oy, foz = (float)oz;
-        ndo = -((fdx * fox + fdy * foy) + fdz * foz);
-        mo = 1.0000002f * fmaxf(fabsf(fox), fmaxf(fabsf(foy), fabsf(foz)));
-        R = S.cl_r + mo;
-        eh = 24.0f * u32 * R;
-        noot = (1.5f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) - ((fox * fox + foy * foy) + foz * foz);
-        off = !(mo < 1e6f) || !((float)a > 0.0f && (float)a < 3.0e38f);
-    } else {
     const double ddx = (double)udx, ddy = (double)udy, ddz = (double)udz;
-    fdx = (float)ddx; fdy = (float)ddy; fdz = (float)ddz;
-    ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
-    mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
-    R = S.cl_r + mo;
-    eh = 17.5f * u32 * R;
-    noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
+    const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+    float ndo = -(float)(ddx * (double)ox + ddy * (double)oy + ddz * (double)oz);
+    const float mo = 1.0000002f * fmaxf(fabsf((float)(double)ox), fmaxf(fabsf((float)(double)oy), fabsf((float)(double)oz)));
+    const float R = S.cl_r + mo;
+    float eh = 17.5f * u32 * R;
+    float noot = (float)((double)(1.03f * u32 * (22.0f * R * R + 6.2f * S.filt_r2max) + 1e-30f) -
                          ((double)ox * (double)ox + (double)oy * (double)oy + (double)oz * (double)oz));
     // origin too far out, or a direction without a finite positive length: no culling at all for this ray
-    off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
-    }
+    const bool off = !(mo < 1e6f) || !((double)a > 0.0 && (double)a < 1.7976931348623157e308);
     if (off) { noot = __int_as_float(0x7f800000); eh = 0.0f; }
     ndo += eh;
     const float2 Dx = make_float2(fdx, fdx), Dy = make_float2(fdy, fdy), Dz = make_float2(fdz, fdz);
-    const float px = kF32Const ? 2.0f * (float)ox : (float)(2.0 * (double)ox), py = kF32Const ? 2.0f * (float)oy : (float)(2.0 * (double)oy),
-                pz = kF32Const ? 2.0f * (float)oz : (float)(2.0 * (double)oz);
+    const float px = (float)(2.0 * (double)ox), py = (float)(2.0 * (double)oy), pz = (float)(2.0 * (double)oz);
     const float2 Px = make_float2(px, px), Py = make_float2(py, py), Pz = make_float2(pz, pz);
     const float2 NDO = make_float2(ndo, ndo), NOOT = make_float2(noot, noot);
     // ---- per-ray constants of the box test ----
@@ -512,9 +492,8 @@ __device__ __forceinline__ void cluster_scan(const DevScene<T>& S, const float4*
         return r;
     };
     const float ix = rcp(fdx), iy = rcp(fdy), iz = rcp(fdz);
-    const float nqx = kF32Const ? -((float)ox * ix) : -(float)((double)ox * (double)ix), nqy = kF32Const ? -((float)oy * iy) : -(float)((double)oy * (double)iy),
-                nqz = kF32Const ? -((float)oz * iz) : -(float)((double)oz * (double)iz);
-    const float ks = (kF32Const ? 24.0f : 16.0f) * u32 * R;
+    const float nqx = -(float)((double)ox * (double)ix), nqy = -(float)((double)oy * (double)iy), nqz = -(float)((double)oz * (double)iz);
+    const float ks = 16.0f * u32 * R;
     const float2 IX = make_float2(ix, ix), IY = make_float2(iy, iy), IZ = make_float2(iz, iz);
     const float2 NQX = make_float2(nqx, nqx), NQY = make_float2(nqy, nqy), NQZ = make_float2(nqz, nqz);
     const float2 AX = make_float2(fabsf(ix), fabsf(ix)), AY = make_float2(fabsf(iy), fabsf(iy)), AZ = make_float2(fabsf(iz), fabsf(iz));
