@@ -118,7 +118,10 @@ def test_camera_defaults():
 
 def test_camera_matches_oracle_bit_for_bit(O):
     for (w, h), kw in (((400, 225), O.RICH_CAMERA), ((1920, 1080), O.RICH_CAMERA), ((3840, 2160), O.RICH_CAMERA),
-                       ((10, 10), dict(focal_length=5, vfov=30.0)), ((7, 13), dict(position=(-2, 2, 1), look_at=(0, 0, -1), vfov=20.0, aperture=.1, focus_distance=3.4))):
+                       ((10, 10), dict(focal_length=5, vfov=30.0)), ((7, 13), dict(position=(-2, 2, 1), look_at=(0, 0, -1), vfov=20.0, aperture=.1, focus_distance=3.4)),
+                       # the default 90 degrees (Go's Tan gives exactly 1 at Pi/4, libm 1 - 2^-53) and angles beyond it
+                       ((640, 360), dict()), ((33, 17), dict(position=(1, 2, 3), vfov=90.0)), ((64, 36), dict(vfov=100.0, focal_length=2)),
+                       ((64, 36), dict(vfov=137.5, look_at=(0.5, -0.25, -1))), ((50, 50), dict(vfov=1.0))):
         oc = O.camera_init(w, h, **kw)
         c = ray.Camera(Position=kw.get("position", (0, 0, 0)), LookAt=kw.get("look_at", (0, 0, 0)), Up=kw.get("up", (0, 0, 0)),
                        VerticalFoV=kw.get("vfov", 0), FocalLength=kw.get("focal_length", 0), FocusDistance=kw.get("focus_distance", 0),
@@ -128,6 +131,26 @@ def test_camera_matches_oracle_bit_for_bit(O):
         for k in ("position", "pixel00", "pixel_x", "pixel_y", "defocus_u", "defocus_v"):
             assert list(getattr(cc, k)) == list(getattr(oc, k)), (w, h, k)
         assert (cc.aperture, cc.focus_distance, cc.focal_length) == (oc.aperture, oc.focus_distance, oc.focal_length)
+
+
+def test_go_tan_is_the_oracles_and_not_libm(O):
+    """Camera.Initialize calls Go's math.Tan (ray/camera.go:85; pure-Go Cephes form on amd64/arm64): the host mirror restates it
+    and agrees with the oracle's restatement bit for bit; libm's tan differs in the last ulp for a quarter of the arguments,
+    the default field of view among them."""
+    import ctypes
+    import math
+    import random
+    lib = O.lib()
+    lib.oracle_go_tan.restype, lib.oracle_go_tan.argtypes = ctypes.c_double, [ctypes.c_double]
+    rnd = random.Random(3)
+    xs = [rnd.uniform(-3.2, 3.2) for _ in range(20000)] + [rnd.uniform(0, 1.6) for _ in range(20000)] + [0.0, math.pi / 4, -math.pi / 4, 1e-9, 1.5707]
+    differ = 0
+    for x in xs:
+        a, b = ray.go_tan(x), lib.oracle_go_tan(x)
+        assert a == b, x
+        differ += a != math.tan(x)
+    assert ray.go_tan(90.0 * (math.pi / 180.0) / 2.0) == 1.0
+    assert differ > 0.1 * len(xs)
 
 
 def test_pixel_center_ray_direction():

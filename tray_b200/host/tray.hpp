@@ -109,6 +109,26 @@ inline Scene RichScene(fortio_rand::Rand& rng, int half = 11) {  // ray/objects.
     return w;
 }
 
+// Go math.Tan (src/math/tan.go: pure-Go Cephes form, no assembly on amd64 / arm64) for |x| < 2^29 -- what Camera.Initialize
+// calls (ray/camera.go:85). Only + - * / on doubles (build with -ffp-contract=off); libm's tan may differ in the last ulp.
+inline double GoTan(double x) {
+    const double PI4A = 7.85398125648498535156e-1, PI4B = 3.77489470793079817668e-8, PI4C = 2.69515142907905952645e-15;
+    const double P0 = -1.30936939181383777646e4, P1 = 1.15351664838587416140e6, P2 = -1.79565251976484877988e7;
+    const double Q1 = 1.36812963470692954678e4, Q2 = -1.32089234440210967447e6, Q3 = 2.50083801823357915839e7, Q4 = -5.38695755929454629881e7;
+    if (x == 0 || std::isnan(x)) return x;
+    if (std::isinf(x)) return std::nan("");
+    const bool sign = x < 0;
+    if (sign) x = -x;
+    uint64_t j = (uint64_t)(x * 0x1.45f306dc9c883p+0);  // 4/Pi, folded like Go folds the constant
+    double y = (double)j;
+    if (j & 1) { j++; y++; }
+    const double z = ((x - y * PI4A) - y * PI4B) - y * PI4C, zz = z * z;
+    if (zz > 1e-14) y = z + z * (zz * (((P0 * zz) + P1) * zz + P2) / ((((zz + Q1) * zz + Q2) * zz + Q3) * zz + Q4));
+    else y = z;
+    if (j & 2) y = -1 / y;
+    return sign ? -y : y;
+}
+
 struct Camera {  // ray/camera.go:9-39
     Vec3 Position, LookAt, Up;
     double VerticalFoV = 0, FocalLength = 0, FocusDistance = 0, Aperture = 0;
@@ -127,7 +147,7 @@ struct Camera {  // ray/camera.go:9-39
         defocusDiskU = SMul(u, defocusRadius);
         defocusDiskV = SMul(v, defocusRadius);
         double theta = VerticalFoV * 0x1.1df46a2529d39p-6;  // Go constant math.Pi/180.0, exactly rounded
-        double viewportHeight = 2.0 * FocalLength * std::tan(theta / 2.0);
+        double viewportHeight = 2.0 * FocalLength * GoTan(theta / 2.0);  // math.Tan as Go computes it (Cephes form), not libm's
         double aspectRatio = (double)width / (double)height;
         double viewportWidth = aspectRatio * viewportHeight;
         Vec3 horizontal = SMul(u, viewportWidth), vertical = SMul(v, -viewportHeight);

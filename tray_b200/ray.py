@@ -150,6 +150,36 @@ def RichScene(rng, half=11):
 # ------------------------------------------------------------------------------------------------
 # Camera (ray/camera.go)
 # ------------------------------------------------------------------------------------------------
+def go_tan(x):
+    """Go math.Tan (src/math/tan.go: pure-Go Cephes form, no assembly on amd64 / arm64) for |x| < 2**29 -- what
+    Camera.Initialize calls (ray/camera.go:85). Only + - * / on doubles, so it is the same on every host; libm's tan may
+    differ in the last ulp, which would move pixel00 and every camera ray with it."""
+    PI4A, PI4B, PI4C = 7.85398125648498535156e-1, 3.77489470793079817668e-8, 2.69515142907905952645e-15
+    P0, P1, P2 = -1.30936939181383777646e4, 1.15351664838587416140e6, -1.79565251976484877988e7
+    Q1, Q2, Q3, Q4 = 1.36812963470692954678e4, -1.32089234440210967447e6, 2.50083801823357915839e7, -5.38695755929454629881e7
+    if x == 0 or x != x:
+        return x
+    if math.isinf(x):
+        return math.nan
+    sign = x < 0
+    if sign:
+        x = -x
+    j = int(x * float.fromhex("0x1.45f306dc9c883p+0"))  # 4/Pi, folded like Go folds the constant
+    y = float(j)
+    if j & 1:
+        j += 1
+        y += 1.0
+    z = ((x - y * PI4A) - y * PI4B) - y * PI4C
+    zz = z * z
+    if zz > 1e-14:
+        y = z + z * (zz * (((P0 * zz) + P1) * zz + P2) / ((((zz + Q1) * zz + Q2) * zz + Q3) * zz + Q4))
+    else:
+        y = z
+    if j & 2:
+        y = -1 / y
+    return -y if sign else y
+
+
 class Camera:
     def __init__(self, Position=(0.0, 0.0, 0.0), LookAt=(0.0, 0.0, 0.0), Up=(0.0, 0.0, 0.0), VerticalFoV=0.0,
                  FocalLength=0.0, FocusDistance=0.0, Aperture=0.0):
@@ -182,7 +212,7 @@ class Camera:
         self.defocusDiskU = SMul(u, defocusRadius)
         self.defocusDiskV = SMul(v, defocusRadius)
         theta = self.VerticalFoV * (math.pi / 180.0)
-        viewportHeight = 2.0 * self.FocalLength * math.tan(theta / 2.0)
+        viewportHeight = 2.0 * self.FocalLength * go_tan(theta / 2.0)  # math.Tan as Go computes it (Cephes form), not libm's
         aspectRatio = float(width) / float(height)
         viewportWidth = aspectRatio * viewportHeight
         horizontal = SMul(u, viewportWidth)
