@@ -153,6 +153,29 @@ def test_go_tan_is_the_oracles_and_not_libm(O):
     assert differ > 0.1 * len(xs)
 
 
+def test_cpp_host_go_tan_matches(tmp_path):
+    """The C++ host mirror (tray_b200/host/tray.hpp) carries the same restatement of Go's Tan: compiled here and compared with
+    the Python one on a spread of arguments (printed as hex floats)."""
+    import math
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "tray_b200")
+    if not os.path.exists(os.path.join(lib_dir, "libtraycuda.so")):
+        pytest.skip("libtraycuda.so not built")
+    xs = [0.0, math.pi / 4, -math.pi / 4, 10.0 * (math.pi / 180.0), 0.5, 1.0, 1.2, 1.5707, 2.0, 3.0, -2.5, 1e-9, 0.008726646259971648]
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "%s/host/tray.hpp"\n#include <cstdio>\nint main() { const double xs[] = {%s};\n'
+                   'for (double x : xs) std::printf("%%a\\n", ray::GoTan(x)); return 0; }\n' % (lib_dir, ", ".join(float(x).hex() for x in xs)))
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), str(src), "-L" + lib_dir, "-ltraycuda", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [float.fromhex(o) for o in out] == [ray.go_tan(x) for x in xs]
+
+
 def test_pixel_center_ray_direction():
     # camera_test.go:177-216: ray through pixel (5,5) = pixel00 + 5*px + 5*py - position
     c = ray.Camera(Position=(0, 0, 0), LookAt=(0, 0, -1), VerticalFoV=90.0)
